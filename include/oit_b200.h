@@ -1,0 +1,197 @@
+/*
+ * oit_b200.h -- C ABI of the B200-native order-independent-transparency library (liboit_b200.so).
+ *
+ * Drop-in boundary for the hot path of nvpro-samples/vk_order_independent_transparency: the stages that
+ * Sample::onRender records between "clear" and "copyOffscreenToBackBuffer" (oitRender.cpp:28-154), i.e.
+ *
+ *     clearTransparent{Simple,LinkedList,Loop,Loop64,Lock}      oit.h:379-425, oitRender.cpp:156-356
+ *     the opaque draw                                           oitRender.cpp:113-122
+ *     drawTransparent{Simple,LinkedList,Loop,Loop64,Lock,Weighted}  (colour pass + barrier + composite)
+ *     copyOffscreenToBackBuffer (MSAA resolve / 2x downsample)  main.cpp:645-774
+ *
+ * Plain C: pointers, sizes and PODs only; every call returns 0 on success or a negative OitResult and never
+ * throws or aborts across the boundary (the reference aborts through NVVK_CHECK / assert, oitRender.cpp:65,147).
+ * One host thread drives one context; a context owns one CUDA device, one stream and all device memory.
+ * There is NO CPU fallback: without a CUDA device every entry point fails with OIT_ERR_CUDA.
+ */
+#ifndef OIT_B200_H
+#define OIT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OIT_B200_ABI_VERSION 1
+
+/* algorithm / antialiasing encodings: identical to shaders/common.h:44-63 */
+enum
+{
+  OIT_SIMPLE     = 0,
+  OIT_LINKEDLIST = 1,
+  OIT_LOOP       = 2,
+  OIT_LOOP64     = 3,
+  OIT_SPINLOCK   = 4,
+  OIT_INTERLOCK  = 5,
+  OIT_WEIGHTED   = 6,
+  OIT_NUM_ALGORITHMS
+};
+enum
+{
+  OIT_AA_NONE     = 0,
+  OIT_AA_MSAA_4X  = 1, /* 4 samples, per-pixel shading, coverage masks in the A-buffer */
+  OIT_AA_SSAA_4X  = 2, /* 4 samples, per-sample shading, A-buffer x4 */
+  OIT_AA_SUPER_4X = 3, /* render at 2W x 2H, LINEAR downsample */
+  OIT_AA_MSAA_8X  = 4,
+  OIT_AA_SSAA_8X  = 5,
+  OIT_NUM_AATYPES
+};
+
+typedef enum OitResult
+{
+  OIT_OK              = 0,
+  OIT_ERR_INVALID_ARG = -1, /* unknown enum, size 0, layers outside {1..32}, null pointer ... */
+  OIT_ERR_CUDA        = -2, /* no device / a CUDA call failed; oit_last_error() has the CUDA string */
+  OIT_ERR_NO_SCENE    = -3, /* draw before oit_set_scene */
+  OIT_ERR_OUT_OF_MEMORY = -4,
+  OIT_ERR_SIZE        = -5, /* host buffer size does not match the device buffer */
+  OIT_ERR_UNSUPPORTED = -6
+} OitResult;
+
+/*
+ * Parameter surface = the reference's State (oit.h:64-82): same names, same integer encodings, same defaults
+ * (see oit_default_config).  The fields after aaType are what the reference takes from its window
+ * (width/height) and what the split-frame multi-GPU mode adds.
+ */
+typedef struct OitConfig
+{
+  uint32_t algorithm;                     /* default OIT_SPINLOCK */
+  uint32_t oitLayers;                     /* OIT_LAYERS, 1..32 (GUI offers 1,2,4,8,16,32: oitGui.cpp:257-270) */
+  int32_t  linkedListAllocatedPerElement; /* linked-list pool = N*W*H[*msaa] nodes (oit.cpp:119-126,148-152) */
+  int32_t  percentTransparent;            /* 0..100; first spheres transparent, last opaque (oitRender.cpp:68-78) */
+  uint32_t tailBlend;
+  uint32_t interlockIsOrdered;            /* both values use the primitive-ordered critical section here */
+  int32_t  numObjects;                    /* only used by oit_generate_scene */
+  int32_t  subdiv;
+  float    scaleMin;
+  float    scaleWidth;
+  uint32_t aaType;
+  uint32_t width;                         /* viewport size before the supersample factor */
+  uint32_t height;
+  int32_t  device;                        /* CUDA device ordinal */
+  /* sort-first split frame: the context renders only the row strips it owns.  Strip k (stripRows rows of the
+     output image) belongs to band k % bandCount.  bandCount = 1 renders the whole frame. */
+  uint32_t bandCount;
+  uint32_t bandIndex;
+  uint32_t stripRows;                     /* multiple of 16; 0 = default (32) */
+  uint32_t reserved[4];
+} OitConfig;
+
+/* shaderio::SceneData, std140, 224 bytes (shaders/common.h:77-92); matrices column-major like glm.
+   viewport and linkedListAllocatedPerElement are overwritten by the library exactly as
+   updateUniformBuffer (main.cpp:628-637) and createFrameImages (oit.cpp:102-152) do. */
+typedef struct OitSceneData
+{
+  float    projViewMatrix[16];
+  float    viewMatrix[16];
+  float    viewMatrixInverseTranspose[16];
+  int32_t  viewport[3];
+  uint32_t linkedListAllocatedPerElement;
+  float    alphaMin;
+  float    alphaWidth;
+  float    pad[2];
+} OitSceneData;
+
+/* stage names follow the reference's profiler sections (oitRender.cpp:158-389) */
+typedef struct OitStats
+{
+  uint64_t fragments;          /* colour-pass invocations of the transparent draw: the metric's F */
+  uint64_t fragmentsStored;
+  uint64_t fragmentsTail;
+  uint64_t opaqueFragments;
+  uint64_t trianglesDrawn;
+  uint64_t trianglesRejected;  /* w<=0, outside the guard band or the depth clip volume */
+  uint64_t llCounter;          /* linked list: final counter value (may exceed the pool) */
+  uint64_t tilePairs;          /* (tile, triangle) pairs binned this frame */
+  uint64_t kernelLaunches;     /* kernels launched by the last oit_render */
+  float    msGeometry;         /* vertex transform + triangle setup + binning */
+  float    msClear;            /* <Tech>Clear + colour/depth clear */
+  float    msOpaque;
+  float    msColor;            /* <Tech>Color (+ LoopDepth) */
+  float    msComposite;        /* <Tech>Composite */
+  float    msResolve;          /* copyOffscreenToBackBuffer */
+  float    msFrame;            /* whole oit_render on the device */
+} OitStats;
+
+/* device/host buffers addressable through oit_download / oit_upload / oit_device_ptr */
+typedef enum OitBuffer
+{
+  OIT_BUF_ABUFFER  = 0, /* layout per technique exactly as oit.cpp:84-163 / the shaders index it */
+  OIT_BUF_AUX      = 1, /* imgAux      R32UI W x H x layers */
+  OIT_BUF_AUXSPIN  = 2, /* imgSpin */
+  OIT_BUF_AUXDEPTH = 3, /* imgDepth */
+  OIT_BUF_COUNTER  = 4, /* imgCounter  1 x 1 */
+  OIT_BUF_COLOR    = 5, /* m_colorImage: BGRA8 sRGB words, [y][x][sample] */
+  OIT_BUF_DEPTH    = 6, /* m_depthImage: float [y][x][sample]; only allocated when something opaque is drawn */
+  OIT_BUF_WACCUM   = 7, /* WBOIT RGBA16F [y][x][sample][4] */
+  OIT_BUF_WREVEAL  = 8, /* WBOIT R16F   [y][x][sample] */
+  OIT_BUF_FINAL    = 9  /* m_viewportImage: BGRA8, width x (rows owned by this band), sRGB-encoded bytes */
+} OitBuffer;
+
+typedef struct OitCtx OitCtx;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int         oit_abi_version(void);
+void        oit_default_config(OitConfig* cfg);                 /* State{} defaults, 1280x720, 1 band */
+int         oit_create(const OitConfig* cfg, OitCtx** out);     /* = updateRendererFromState(true,true), main.cpp:130-250 */
+int         oit_destroy(OitCtx* ctx);
+const char* oit_last_error(const OitCtx* ctx);                  /* ctx may be NULL: error of the last failed create */
+int         oit_get_config(const OitCtx* ctx, OitConfig* out);
+/* derived sizes: render-target width/height (after supersample), msaa, sampleShading, rows owned by this band */
+int         oit_get_dims(const OitCtx* ctx, uint32_t* bufW, uint32_t* bufH, uint32_t* msaa, uint32_t* sampleShading,
+                         uint32_t* localRows);
+
+/* ---- scene: what initScene uploads (main.cpp:334-417) ------------------------------------------------------ */
+/* host pointers, copied.  Vertex = pos3f, normal3f, colour4f, 40-byte stride (utilities_vk.h:48-61) */
+int oit_set_scene(OitCtx* ctx, const void* vertices, uint32_t nVerts, const uint32_t* indices, uint32_t nIndices,
+                  uint32_t indicesPerObject);
+/* device pointers on ctx's device, NOT copied; the caller keeps them alive */
+int oit_set_scene_device(OitCtx* ctx, const void* dVertices, uint32_t nVerts, const uint32_t* dIndices, uint32_t nIndices,
+                         uint32_t indicesPerObject);
+/* host-side scene generator + camera of the sample (harness) */
+int oit_scene_sizes(const OitConfig* cfg, uint32_t* nVerts, uint32_t* nIndices, uint32_t* indicesPerObject);
+int oit_generate_scene(const OitConfig* cfg, void* vertices, uint32_t* indices);
+int oit_default_camera(uint32_t width, uint32_t height, float fovDeg, const float eye[3], const float center[3],
+                       const float up[3], float zNear, float zFar, OitSceneData* out);
+
+/* ---- frame -------------------------------------------------------------------------------------------- */
+/* Sample::onRender (oitRender.cpp:28-154): clear, opaque, transparent colour pass(es), composite, resolve.
+   Synchronous: returns when the frame is complete on the device. */
+int oit_render(OitCtx* ctx, const OitSceneData* ubo);
+/* the same stage by stage, for tests and for hosts that interleave their own work (each is asynchronous on the
+   context's stream; oit_synchronize waits) */
+int oit_set_scene_data(OitCtx* ctx, const OitSceneData* ubo);   /* updateUniformBuffer */
+int oit_begin_frame(OitCtx* ctx);          /* vertex stage + binning + clearTransparent* + render-pass clears */
+int oit_draw_opaque(OitCtx* ctx);          /* oitRender.cpp:113-122 */
+int oit_draw_transparent(OitCtx* ctx);     /* colour pass(es) of drawTransparent*, up to the fragment barrier */
+int oit_composite(OitCtx* ctx);            /* the full-screen composite draw of drawTransparent* */
+int oit_resolve(OitCtx* ctx);              /* copyOffscreenToBackBuffer */
+int oit_synchronize(OitCtx* ctx);
+
+/* ---- results / dumps ------------------------------------------------------------------------------------- */
+int   oit_buffer_size(const OitCtx* ctx, OitBuffer which, size_t* bytes);
+int   oit_download(OitCtx* ctx, OitBuffer which, void* host, size_t bytes);   /* A-buffer dump etc. */
+int   oit_upload(OitCtx* ctx, OitBuffer which, const void* host, size_t bytes); /* composite-from-dump */
+void* oit_device_ptr(OitCtx* ctx, OitBuffer which);                          /* NULL if not allocated */
+/* convenience == oit_download(OIT_BUF_FINAL): BGRA8 rows owned by this band, top to bottom */
+int   oit_read_color(OitCtx* ctx, void* bgra8, size_t bytes);
+int   oit_get_stats(OitCtx* ctx, OitStats* out);
+void* oit_stream(OitCtx* ctx);             /* the cudaStream_t the context launches on */
+/* global row index of local row r of this band (for reassembling the gathered strips) */
+int   oit_local_row_to_global(const OitCtx* ctx, uint32_t localRow, uint32_t* globalRow);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OIT_B200_H */

@@ -276,7 +276,7 @@ void transformVertices(OracleCtx* c)
       const float nx = clip[0] * t.invw, ny = clip[1] * t.invw;
       t.z            = clip[2] * t.invw;
       const float xs = fmaf(nx, hw, hw), ys = fmaf(ny, hh, hh);
-      if(!(fabsf(xs) < 4194304.f) || !(fabsf(ys) < 4194304.f) || !(t.z >= 0.f) || !(t.z <= 1.f))
+      if(!(fabsf(xs) < 2097152.f) || !(fabsf(ys) < 2097152.f) || !(t.z >= 0.f) || !(t.z <= 1.f))
         t.valid = false;  // outside the guard band / depth clip volume: triangle is rejected
       else
       {
@@ -621,7 +621,7 @@ bool setupTri(const OracleCtx* c, uint32_t i0, uint32_t i1, uint32_t i2, bool cu
     st.rejected++;
     return false;
   }
-  int64_t area2 = (int64_t)(v1.x - v0.x) * (v2.y - v0.y) - (int64_t)(v2.x - v0.x) * (v1.y - v0.y);
+  int64_t area2 = ((int64_t)v1.x - v0.x) * ((int64_t)v2.y - v0.y) - ((int64_t)v2.x - v0.x) * ((int64_t)v1.y - v0.y);
   if(area2 == 0)
     return false;
   /* Vulkan: a = -1/2 sum(x_i*y_i+1 - x_i+1*y_i); positive = front for COUNTER_CLOCKWISE => front iff area2 < 0 */

@@ -1,0 +1,843 @@
+// oit_api.cu -- host side of liboit_b200.so: context, device memory, and the frame skeleton of Sample::onRender
+// (oitRender.cpp:28-154) expressed as kernel launches on one CUDA stream.  See include/oit_b200.h for the contract.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "oit_internal.h"
+
+using namespace oit;
+
+namespace {
+thread_local std::string g_createError;
+
+double srgbToLinearD(double c) { return c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4); }
+
+// tables[0..255] = sRGB8 code -> linear, tables[256..511] = encode thresholds (thr[0] = -inf)
+void buildTables(float* t)
+{
+  for(int v = 0; v < 256; v++)
+    t[v] = (float)srgbToLinearD(v / 255.0);
+  t[256] = -std::numeric_limits<float>::infinity();
+  for(int k = 1; k < 256; k++)
+    t[256 + k] = (float)srgbToLinearD((k - 0.5) / 255.0);
+}
+uint32_t hostEnc8(const float* t, float c)
+{
+  uint32_t k = 0;
+  for(uint32_t step = 128; step; step >>= 1)
+    if(c >= t[256 + k + step])
+      k += step;
+  return k;
+}
+
+struct DevBuf
+{
+  void*  p     = nullptr;
+  size_t bytes = 0;
+};
+
+enum EventId
+{
+  EV_START = 0,
+  EV_GEOM,
+  EV_CLEAR,
+  EV_OPAQUE,
+  EV_COLOR,
+  EV_COMPOSITE,
+  EV_RESOLVE,
+  NUM_EVENTS
+};
+}  // namespace
+
+struct OitCtx
+{
+  OitConfig    cfg{};
+  int          msaa = 1, supersample = 1;
+  bool         sampleShading = false, coverage = false;
+  uint32_t     bufW = 0, bufH = 0, localBufH = 0, localOutH = 0;
+  uint32_t     stripRows = 32;
+  std::string  error;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev[NUM_EVENTS]{};
+  bool         evRecorded[NUM_EVENTS]{};
+  FrameParams  fp{};
+  OitSceneData ubo{};
+  bool         haveUbo = false;
+  // buffers
+  DevBuf abuf, aux, spin, adepth, counter, color, depth, wacc, wrev, fin, tables, stats;
+  // scene
+  DevBuf   verts, indices, tv;
+  bool     sceneOwned = false;
+  uint32_t nVerts = 0, nIndices = 0, idxPerObj = 0;
+  // binning (0 = transparent draw, 1 = opaque draw)
+  BinBuffers bins[2]{};
+  uint32_t   pairTotal[2]{};
+  int        sortedBuf[2]{};
+  uint32_t*  hostScalar = nullptr;  // pinned
+  OitStats   lastStats{};
+  uint64_t   launches = 0;
+};
+
+namespace {
+
+int fail(OitCtx* c, int code, const std::string& msg)
+{
+  if(c)
+    c->error = msg;
+  else
+    g_createError = msg;
+  return code;
+}
+#define CUDA_TRY(ctx, call)                                                                                                      \
+  do                                                                                                                             \
+  {                                                                                                                              \
+    cudaError_t e__ = (call);                                                                                                    \
+    if(e__ != cudaSuccess)                                                                                                       \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? OIT_ERR_OUT_OF_MEMORY : OIT_ERR_CUDA,                                   \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                                                          \
+  } while(0)
+
+int devAlloc(OitCtx* c, DevBuf& b, size_t bytes)
+{
+  if(b.p)
+  {
+    cudaFree(b.p);
+    b.p = nullptr;
+  }
+  b.bytes = bytes;
+  if(bytes == 0)
+    return OIT_OK;
+  CUDA_TRY(c, cudaMalloc(&b.p, bytes));
+  return OIT_OK;
+}
+void devFree(DevBuf& b)
+{
+  if(b.p)
+    cudaFree(b.p);
+  b.p     = nullptr;
+  b.bytes = 0;
+}
+
+void freeBins(BinBuffers& b)
+{
+  cudaFree(b.counts);
+  cudaFree(b.pairKey[0]);
+  cudaFree(b.pairKey[1]);
+  cudaFree(b.pairVal[0]);
+  cudaFree(b.pairVal[1]);
+  cudaFree(b.tileStart);
+  cudaFree(b.scratch);
+  b = BinBuffers{};
+}
+
+// (re)allocates the binning buffers of one draw for `triCount` triangles and `pairCapacity` pairs
+int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
+{
+  const size_t numTiles = (size_t)c->fp.tilesX * c->fp.tileRowsLocal;
+  freeBins(b);
+  b.pairCapacity = pairCapacity;
+  b.triCapacity  = triCount;
+  b.scratchWords = binScratchWords(triCount, pairCapacity, numTiles);
+  CUDA_TRY(c, cudaMalloc(&b.counts, (triCount + 1) * sizeof(uint32_t)));
+  for(int i = 0; i < 2; i++)
+  {
+    CUDA_TRY(c, cudaMalloc(&b.pairKey[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
+  }
+  CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
+  return OIT_OK;
+}
+
+void splitObjects(const OitCtx* c, uint32_t& numTransparent, uint32_t& numOpaque)
+{
+  // oitRender.cpp:68-78
+  const int numObjects = c->idxPerObj ? (int)(c->nIndices / c->idxPerObj) : 0;
+  int       nt         = (int)(((long long)numObjects * c->cfg.percentTransparent) / 100);
+  nt                   = std::min(std::max(nt, 0), numObjects);
+  numTransparent       = (uint32_t)nt;
+  numOpaque            = (uint32_t)(numObjects - nt);
+}
+
+void record(OitCtx* c, int id)
+{
+  cudaEventRecord(c->ev[id], c->stream);
+  c->evRecorded[id] = true;
+}
+
+DevBuf* bufferOf(OitCtx* c, OitBuffer which)
+{
+  switch(which)
+  {
+    case OIT_BUF_ABUFFER: return &c->abuf;
+    case OIT_BUF_AUX: return &c->aux;
+    case OIT_BUF_AUXSPIN: return &c->spin;
+    case OIT_BUF_AUXDEPTH: return &c->adepth;
+    case OIT_BUF_COUNTER: return &c->counter;
+    case OIT_BUF_COLOR: return &c->color;
+    case OIT_BUF_DEPTH: return &c->depth;
+    case OIT_BUF_WACCUM: return &c->wacc;
+    case OIT_BUF_WREVEAL: return &c->wrev;
+    case OIT_BUF_FINAL: return &c->fin;
+  }
+  return nullptr;
+}
+
+// bins one draw range; synchronises the stream once to learn the pair count
+int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullBack)
+{
+  BinBuffers&    b        = c->bins[which];
+  const uint32_t triPerObj = c->idxPerObj / 3;
+  const uint32_t firstTri = firstObj * triPerObj, triCount = numObj * triPerObj;
+  c->pairTotal[which]     = 0;
+  if(triCount == 0)
+    return OIT_OK;
+  c->launches += launchBinCount(c->fp, b, firstTri, triCount, cullBack, c->stream);
+  CUDA_TRY(c, cudaMemcpyAsync(c->hostScalar, b.counts + triCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const uint32_t total = *c->hostScalar;
+  if(total > b.pairCapacity)
+  {
+    // grow: keep the scanned counts (they are the emit offsets)
+    const size_t newCap = (size_t)total + total / 4 + 1024;
+    for(int i = 0; i < 2; i++)
+    {
+      cudaFree(b.pairKey[i]);
+      cudaFree(b.pairVal[i]);
+      b.pairKey[i] = b.pairVal[i] = nullptr;
+      CUDA_TRY(c, cudaMalloc(&b.pairKey[i], newCap * sizeof(uint32_t)));
+      CUDA_TRY(c, cudaMalloc(&b.pairVal[i], newCap * sizeof(uint32_t)));
+    }
+    cudaFree(b.scratch);
+    b.scratch      = nullptr;
+    b.pairCapacity = newCap;
+    b.scratchWords = binScratchWords(triCount, newCap, 0);
+    CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
+  }
+  c->launches += launchBinEmitSort(c->fp, b, firstTri, triCount, cullBack, total, &c->sortedBuf[which], c->stream);
+  c->pairTotal[which] = total;
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+void useBins(OitCtx* c, int which)
+{
+  c->fp.pairTri   = c->bins[which].pairVal[c->sortedBuf[which]];
+  c->fp.tileStart = c->bins[which].tileStart;
+}
+
+int ensureSceneBins(OitCtx* c)
+{
+  uint32_t nt, no;
+  splitObjects(c, nt, no);
+  const size_t triPerObj = c->idxPerObj / 3;
+  const size_t need[2]   = {nt * triPerObj, no * triPerObj};
+  for(int i = 0; i < 2; i++)
+  {
+    if(need[i] == 0)
+      continue;
+    if(c->bins[i].counts == nullptr || c->bins[i].triCapacity < need[i])
+    {
+      const size_t cap = std::max<size_t>(need[i] * 2, 1u << 16);
+      const int    r   = allocBins(c, c->bins[i], need[i], cap);
+      if(r != OIT_OK)
+        return r;
+    }
+  }
+  return OIT_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+extern "C" {
+
+int oit_abi_version(void) { return OIT_B200_ABI_VERSION; }
+
+void oit_default_config(OitConfig* cfg)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->algorithm                     = OIT_SPINLOCK;  // oit.h:66-76
+  cfg->oitLayers                     = 8;
+  cfg->linkedListAllocatedPerElement = 10;
+  cfg->percentTransparent            = 100;
+  cfg->tailBlend                     = 1;
+  cfg->interlockIsOrdered            = 1;
+  cfg->numObjects                    = 1024;
+  cfg->subdiv                        = 16;
+  cfg->scaleMin                      = 0.1f;
+  cfg->scaleWidth                    = 0.9f;
+  cfg->aaType                        = OIT_AA_NONE;
+  cfg->width                         = 1280;
+  cfg->height                        = 720;
+  cfg->device                        = 0;
+  cfg->bandCount                     = 1;
+  cfg->bandIndex                     = 0;
+  cfg->stripRows                     = 32;
+}
+
+const char* oit_last_error(const OitCtx* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int oit_create(const OitConfig* cfg, OitCtx** out)
+{
+  if(!cfg || !out)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if(cfg->algorithm >= OIT_NUM_ALGORITHMS)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "unknown algorithm");
+  if(cfg->aaType >= OIT_NUM_AATYPES)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "unknown aaType");
+  if(cfg->oitLayers < 1 || cfg->oitLayers > 32)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "oitLayers must be in 1..32");
+  if(cfg->width == 0 || cfg->height == 0 || cfg->width > 16384 || cfg->height > 16384)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "bad target size");
+  if(cfg->linkedListAllocatedPerElement < 1 && cfg->algorithm == OIT_LINKEDLIST)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "linkedListAllocatedPerElement must be >= 1");
+  if(cfg->percentTransparent < 0 || cfg->percentTransparent > 100)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "percentTransparent must be in 0..100");
+  const uint32_t bandCount = cfg->bandCount ? cfg->bandCount : 1;
+  if(cfg->bandIndex >= bandCount)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "bandIndex >= bandCount");
+  const uint32_t stripRows = cfg->stripRows ? cfg->stripRows : 32;
+  if(stripRows % TILE_H)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "stripRows must be a multiple of 16");
+
+  int nDev = 0;
+  if(cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+    return fail(nullptr, OIT_ERR_CUDA, "no CUDA device: liboit_b200 has no CPU fallback");
+  if(cfg->device < 0 || cfg->device >= nDev)
+    return fail(nullptr, OIT_ERR_INVALID_ARG, "bad device ordinal");
+
+  OitCtx* c = new(std::nothrow) OitCtx();
+  if(!c)
+    return fail(nullptr, OIT_ERR_OUT_OF_MEMORY, "host allocation failed");
+  c->cfg           = *cfg;
+  c->cfg.bandCount = bandCount;
+  c->cfg.stripRows = stripRows;
+  c->stripRows     = stripRows;
+  // State::recomputeAntialiasingSettings (oit.h:88-115)
+  switch(cfg->aaType)
+  {
+    case OIT_AA_MSAA_4X: c->msaa = 4; break;
+    case OIT_AA_SSAA_4X: c->msaa = 4; c->sampleShading = true; break;
+    case OIT_AA_SUPER_4X: c->supersample = 2; break;
+    case OIT_AA_MSAA_8X: c->msaa = 8; break;
+    case OIT_AA_SSAA_8X: c->msaa = 8; c->sampleShading = true; break;
+    default: break;
+  }
+  c->coverage = c->msaa > 1 && !c->sampleShading;
+  c->bufW     = cfg->width * c->supersample;
+  c->bufH     = cfg->height * c->supersample;
+
+  auto cleanupFail = [&](int code) {
+    g_createError = c->error;
+    oit_destroy(c);
+    return code;
+  };
+#define CREATE_TRY(call)                                                                                                         \
+  do                                                                                                                             \
+  {                                                                                                                              \
+    int r__ = (call);                                                                                                            \
+    if(r__ != OIT_OK)                                                                                                            \
+      return cleanupFail(r__);                                                                                                   \
+  } while(0)
+#define CREATE_CUDA(call)                                                                                                        \
+  do                                                                                                                             \
+  {                                                                                                                              \
+    cudaError_t e__ = (call);                                                                                                    \
+    if(e__ != cudaSuccess)                                                                                                       \
+    {                                                                                                                            \
+      c->error = std::string(#call) + ": " + cudaGetErrorString(e__);                                                            \
+      return cleanupFail(e__ == cudaErrorMemoryAllocation ? OIT_ERR_OUT_OF_MEMORY : OIT_ERR_CUDA);                                \
+    }                                                                                                                            \
+  } while(0)
+
+  CREATE_CUDA(cudaSetDevice(cfg->device));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for(int i = 0; i < NUM_EVENTS; i++)
+    CREATE_CUDA(cudaEventCreate(&c->ev[i]));
+  CREATE_CUDA(cudaMallocHost(&c->hostScalar, 64));
+
+  // tile / band geometry
+  FrameParams& fp    = c->fp;
+  fp.W               = (int)c->bufW;
+  fp.H               = (int)c->bufH;
+  fp.msaa            = c->msaa;
+  fp.sampleShading   = c->sampleShading ? 1 : 0;
+  fp.coverage        = c->coverage ? 1 : 0;
+  fp.L               = (int)cfg->oitLayers;
+  fp.tailBlend       = cfg->tailBlend ? 1 : 0;
+  fp.layers          = c->sampleShading ? c->msaa : 1;
+  fp.tilesX          = (fp.W + TILE_W - 1) / TILE_W;
+  fp.tileRowsGlobal  = (fp.H + TILE_H - 1) / TILE_H;
+  fp.stripTileRows   = (int)(stripRows * c->supersample) / TILE_H;
+  fp.bandCount       = (int)bandCount;
+  fp.bandIndex       = (int)cfg->bandIndex;
+  fp.tileRowsLocal   = 0;
+  uint32_t localBufH = 0;
+  for(int R = 0; R < fp.tileRowsGlobal; R++)
+    if(tileRowOwner(R, fp.stripTileRows, fp.bandCount) == fp.bandIndex)
+    {
+      fp.tileRowsLocal++;
+      localBufH += (uint32_t)std::min(TILE_H, fp.H - R * TILE_H);
+    }
+  c->localBufH = localBufH;
+  c->localOutH = localBufH / c->supersample;
+  fp.localH    = (int)localBufH;
+
+  // createFrameImages (oit.cpp:84-163), sized for the rows this band owns
+  const size_t P     = (size_t)c->bufW * localBufH;
+  size_t       words = 0;
+  fp.capacity        = 0;
+  switch(cfg->algorithm)
+  {
+    case OIT_SIMPLE:
+    case OIT_SPINLOCK:
+    case OIT_INTERLOCK: words = P * cfg->oitLayers * (c->coverage ? 4 : 2); break;
+    case OIT_LINKEDLIST: {
+      words = P * (size_t)cfg->linkedListAllocatedPerElement * 4;
+      // uint32 arithmetic like the reference (oit.cpp:125,151); node indices must stay below 2^31 (oitLinkedList.frag.glsl:82)
+      const unsigned long long cap = (unsigned long long)cfg->linkedListAllocatedPerElement * P * fp.layers;
+      if(cap >= (1ull << 31))
+      {
+        c->error = "linked-list pool would exceed 2^31 nodes";
+        return cleanupFail(OIT_ERR_INVALID_ARG);
+      }
+      fp.capacity = (uint32_t)cap;
+      break;
+    }
+    case OIT_LOOP: words = P * cfg->oitLayers * 2; break;
+    case OIT_LOOP64: words = P * cfg->oitLayers * 2; break;
+    default: break;
+  }
+  words *= fp.layers;
+  // the linked-list pool has at least node 0 + one usable node so that the index arithmetic is always in bounds
+  CREATE_TRY(devAlloc(c, c->abuf, std::max<size_t>(words, 4) * 4));
+  if(cfg->algorithm != OIT_WEIGHTED)
+    CREATE_TRY(devAlloc(c, c->aux, P * fp.layers * 4));
+  if(cfg->algorithm == OIT_SPINLOCK)
+    CREATE_TRY(devAlloc(c, c->spin, P * fp.layers * 4));
+  if(cfg->algorithm == OIT_SPINLOCK || cfg->algorithm == OIT_INTERLOCK)
+    CREATE_TRY(devAlloc(c, c->adepth, P * fp.layers * 4));
+  if(cfg->algorithm == OIT_LINKEDLIST)
+    CREATE_TRY(devAlloc(c, c->counter, 4));
+  if(cfg->algorithm == OIT_WEIGHTED)
+  {
+    CREATE_TRY(devAlloc(c, c->wacc, P * c->msaa * 8));
+    CREATE_TRY(devAlloc(c, c->wrev, ((P * c->msaa + 1) / 2) * 4));
+  }
+  CREATE_TRY(devAlloc(c, c->color, P * c->msaa * 4));
+  if(cfg->percentTransparent < 100)
+    CREATE_TRY(devAlloc(c, c->depth, P * c->msaa * 4));
+  CREATE_TRY(devAlloc(c, c->fin, std::max<size_t>((size_t)cfg->width * c->localOutH, 1) * 4));
+  CREATE_TRY(devAlloc(c, c->tables, 512 * sizeof(float)));
+  CREATE_TRY(devAlloc(c, c->stats, NUM_STAT_SLOTS * sizeof(unsigned long long)));
+  float tables[512];
+  buildTables(tables);
+  CREATE_CUDA(cudaMemcpy(c->tables.p, tables, sizeof(tables), cudaMemcpyHostToDevice));
+  CREATE_CUDA(cudaMemset(c->stats.p, 0, c->stats.bytes));
+  // clear colour (0.2, 0.2, 0.2, 0.2) linear -> B8G8R8A8_SRGB (oitRender.cpp:90)
+  const uint32_t rgb = hostEnc8(tables, 0.2f);
+  fp.clearColor      = rgb | (rgb << 8) | (rgb << 16) | ((uint32_t)rintf(0.2f * 255.0f) << 24);
+
+  fp.abuf    = (uint32_t*)c->abuf.p;
+  fp.aux     = (uint32_t*)c->aux.p;
+  fp.spin    = (uint32_t*)c->spin.p;
+  fp.adepth  = (uint32_t*)c->adepth.p;
+  fp.counter = (uint32_t*)c->counter.p;
+  fp.color   = (uint32_t*)c->color.p;
+  fp.depth   = (float*)c->depth.p;
+  fp.wacc    = (uint16_t*)c->wacc.p;
+  fp.wrev    = (uint16_t*)c->wrev.p;
+  fp.fin     = (uint32_t*)c->fin.p;
+  fp.tables  = (const float*)c->tables.p;
+  fp.stats   = (unsigned long long*)c->stats.p;
+  fp.alphaMin   = 0.2f;
+  fp.alphaWidth = 0.3f;
+  *out          = c;
+  return OIT_OK;
+#undef CREATE_TRY
+#undef CREATE_CUDA
+}
+
+int oit_destroy(OitCtx* c)
+{
+  if(!c)
+    return OIT_OK;
+  cudaSetDevice(c->cfg.device);
+  if(c->stream)
+    cudaStreamSynchronize(c->stream);
+  for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
+                   &c->tables, &c->stats, &c->tv})
+    devFree(*b);
+  if(c->sceneOwned)
+  {
+    devFree(c->verts);
+    devFree(c->indices);
+  }
+  freeBins(c->bins[0]);
+  freeBins(c->bins[1]);
+  for(int i = 0; i < NUM_EVENTS; i++)
+    if(c->ev[i])
+      cudaEventDestroy(c->ev[i]);
+  if(c->hostScalar)
+    cudaFreeHost(c->hostScalar);
+  if(c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+  return OIT_OK;
+}
+
+int oit_get_config(const OitCtx* c, OitConfig* out)
+{
+  if(!c || !out)
+    return OIT_ERR_INVALID_ARG;
+  *out = c->cfg;
+  return OIT_OK;
+}
+
+int oit_get_dims(const OitCtx* c, uint32_t* bufW, uint32_t* bufH, uint32_t* msaa, uint32_t* sampleShading, uint32_t* localRows)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  if(bufW)
+    *bufW = c->bufW;
+  if(bufH)
+    *bufH = c->bufH;
+  if(msaa)
+    *msaa = (uint32_t)c->msaa;
+  if(sampleShading)
+    *sampleShading = c->sampleShading ? 1u : 0u;
+  if(localRows)
+    *localRows = c->localOutH;
+  return OIT_OK;
+}
+
+static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t indicesPerObject)
+{
+  c->nVerts    = nVerts;
+  c->nIndices  = nIndices;
+  c->idxPerObj = indicesPerObject;
+  int r        = devAlloc(c, c->tv, (size_t)nVerts * sizeof(TVert));
+  if(r != OIT_OK)
+    return r;
+  c->fp.verts   = (const float*)c->verts.p;
+  c->fp.indices = (const uint32_t*)c->indices.p;
+  c->fp.tv      = (TVert*)c->tv.p;
+  c->fp.nVerts  = nVerts;
+  return ensureSceneBins(c);
+}
+
+int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32_t* indices, uint32_t nIndices, uint32_t indicesPerObject)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  if(!vertices || !indices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
+    return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  for(uint32_t i = 0; i < nIndices; i++)
+    if(indices[i] >= nVerts)
+      return fail(c, OIT_ERR_INVALID_ARG, "index out of range");
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(!c->sceneOwned)
+  {
+    c->verts   = DevBuf{};
+    c->indices = DevBuf{};
+  }
+  c->sceneOwned = true;
+  if(c->verts.bytes != (size_t)nVerts * 40)
+  {
+    int r = devAlloc(c, c->verts, (size_t)nVerts * 40);
+    if(r != OIT_OK)
+      return r;
+  }
+  if(c->indices.bytes != (size_t)nIndices * 4)
+  {
+    int r = devAlloc(c, c->indices, (size_t)nIndices * 4);
+    if(r != OIT_OK)
+      return r;
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->verts.p, vertices, (size_t)nVerts * 40, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->indices.p, indices, (size_t)nIndices * 4, cudaMemcpyHostToDevice, c->stream));
+  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != indicesPerObject || !c->tv.p)
+    return installScene(c, nVerts, nIndices, indicesPerObject);
+  c->fp.verts   = (const float*)c->verts.p;
+  c->fp.indices = (const uint32_t*)c->indices.p;
+  return OIT_OK;
+}
+
+int oit_set_scene_device(OitCtx* c, const void* dVertices, uint32_t nVerts, const uint32_t* dIndices, uint32_t nIndices, uint32_t indicesPerObject)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  if(!dVertices || !dIndices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
+    return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(c->sceneOwned)
+  {
+    devFree(c->verts);
+    devFree(c->indices);
+  }
+  c->sceneOwned    = false;
+  c->verts.p       = const_cast<void*>(dVertices);
+  c->verts.bytes   = (size_t)nVerts * 40;
+  c->indices.p     = const_cast<uint32_t*>(dIndices);
+  c->indices.bytes = (size_t)nIndices * 4;
+  return installScene(c, nVerts, nIndices, indicesPerObject);
+}
+
+int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
+{
+  if(!c || !ubo)
+    return OIT_ERR_INVALID_ARG;
+  c->ubo = *ubo;
+  // updateUniformBuffer (main.cpp:628-637) + createFrameImages (oit.cpp:102-152) own these fields
+  c->ubo.viewport[0] = (int32_t)c->bufW;
+  c->ubo.viewport[1] = (int32_t)c->bufH;
+  c->ubo.viewport[2] = (int32_t)(c->bufW * c->bufH);
+  c->ubo.linkedListAllocatedPerElement =
+      c->cfg.algorithm == OIT_LINKEDLIST ? c->fp.capacity : c->cfg.oitLayers * (uint32_t)c->fp.layers;
+  memcpy(c->fp.projView, ubo->projViewMatrix, sizeof(float) * 16);
+  memcpy(c->fp.view, ubo->viewMatrix, sizeof(float) * 16);
+  c->fp.alphaMin   = ubo->alphaMin;
+  c->fp.alphaWidth = ubo->alphaWidth;
+  c->haveUbo       = true;
+  return OIT_OK;
+}
+
+int oit_begin_frame(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  if(!c->verts.p || !c->indices.p)
+    return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
+  if(!c->haveUbo)
+    return fail(c, OIT_ERR_INVALID_ARG, "oit_set_scene_data has not been called");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  c->launches = 0;
+  for(bool& b : c->evRecorded)
+    b = false;
+  record(c, EV_START);
+  CUDA_TRY(c, cudaMemsetAsync(c->stats.p, 0, c->stats.bytes, c->stream));
+  // vertex stage + binning of both draws
+  c->launches += launchTransformVertices(c->fp, c->stream);
+  uint32_t nt, no;
+  splitObjects(c, nt, no);
+  int r = ensureSceneBins(c);
+  if(r != OIT_OK)
+    return r;
+  if((r = binDraw(c, 0, 0, nt, false)) != OIT_OK)
+    return r;
+  if((r = binDraw(c, 1, nt, no, true)) != OIT_OK)
+    return r;
+  record(c, EV_GEOM);
+  // clearTransparent* + colour/depth clear
+  c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream);
+  record(c, EV_CLEAR);
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+int oit_draw_opaque(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(c->pairTotal[1] > 0 && c->fp.depth)
+  {
+    useBins(c, 1);
+    c->launches += launchRaster(c->fp, PASS_OPAQUE, c->stream);
+  }
+  record(c, EV_OPAQUE);
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+int oit_draw_transparent(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(c->pairTotal[0] > 0)
+  {
+    useBins(c, 0);
+    switch(c->cfg.algorithm)
+    {
+      case OIT_SIMPLE: c->launches += launchRaster(c->fp, PASS_SIMPLE, c->stream); break;
+      case OIT_LINKEDLIST: c->launches += launchRaster(c->fp, PASS_LINKEDLIST, c->stream); break;
+      case OIT_LOOP:
+        c->launches += launchRaster(c->fp, PASS_LOOP_DEPTH, c->stream);  // oitRender.cpp:269-279
+        c->launches += launchRaster(c->fp, PASS_LOOP_COLOR, c->stream);
+        break;
+      case OIT_LOOP64: c->launches += launchRaster(c->fp, PASS_LOOP64, c->stream); break;
+      case OIT_SPINLOCK: c->launches += launchRaster(c->fp, PASS_SPINLOCK, c->stream); break;
+      case OIT_INTERLOCK: c->launches += launchRaster(c->fp, PASS_INTERLOCK, c->stream); break;
+      case OIT_WEIGHTED: c->launches += launchRaster(c->fp, PASS_WEIGHTED, c->stream); break;
+    }
+  }
+  record(c, EV_COLOR);
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+int oit_composite(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  c->launches += launchComposite(c->fp, (int)c->cfg.algorithm, c->stream);
+  record(c, EV_COMPOSITE);
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+int oit_resolve(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  c->launches += launchResolve(c->fp, c->supersample, (int)c->cfg.width, (int)c->localOutH, c->stream);
+  record(c, EV_RESOLVE);
+  CUDA_TRY(c, cudaGetLastError());
+  return OIT_OK;
+}
+
+int oit_synchronize(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return OIT_OK;
+}
+
+int oit_render(OitCtx* c, const OitSceneData* ubo)
+{
+  int r;
+  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
+    return r;
+  if((r = oit_begin_frame(c)) != OIT_OK)
+    return r;
+  if((r = oit_draw_opaque(c)) != OIT_OK)
+    return r;
+  if((r = oit_draw_transparent(c)) != OIT_OK)
+    return r;
+  if((r = oit_composite(c)) != OIT_OK)
+    return r;
+  if((r = oit_resolve(c)) != OIT_OK)
+    return r;
+  return oit_synchronize(c);
+}
+
+int oit_get_stats(OitCtx* c, OitStats* out)
+{
+  if(!c || !out)
+    return OIT_ERR_INVALID_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  unsigned long long h[NUM_STAT_SLOTS];
+  CUDA_TRY(c, cudaMemcpy(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+  OitStats s{};
+  s.fragments         = h[STAT_FRAGMENTS];
+  s.fragmentsStored   = h[STAT_STORED];
+  s.fragmentsTail     = h[STAT_TAIL];
+  s.opaqueFragments   = h[STAT_OPAQUE];
+  s.trianglesRejected = h[STAT_REJECTED];
+  uint32_t nt, no;
+  splitObjects(c, nt, no);
+  s.trianglesDrawn = (uint64_t)nt * (c->idxPerObj / 3);
+  s.tilePairs      = (uint64_t)c->pairTotal[0] + c->pairTotal[1];
+  s.kernelLaunches = c->launches;
+  if(c->counter.p)
+  {
+    uint32_t v = 0;
+    CUDA_TRY(c, cudaMemcpy(&v, c->counter.p, 4, cudaMemcpyDeviceToHost));
+    s.llCounter = v;
+  }
+  auto ms = [&](int a, int b) {
+    float t = 0.f;
+    if(c->evRecorded[a] && c->evRecorded[b] && cudaEventElapsedTime(&t, c->ev[a], c->ev[b]) == cudaSuccess)
+      return t;
+    return 0.f;
+  };
+  s.msGeometry  = ms(EV_START, EV_GEOM);
+  s.msClear     = ms(EV_GEOM, EV_CLEAR);
+  s.msOpaque    = ms(EV_CLEAR, EV_OPAQUE);
+  s.msColor     = ms(EV_OPAQUE, EV_COLOR);
+  s.msComposite = ms(EV_COLOR, EV_COMPOSITE);
+  s.msResolve   = ms(EV_COMPOSITE, EV_RESOLVE);
+  s.msFrame     = ms(EV_START, EV_RESOLVE);
+  c->lastStats  = s;
+  *out          = s;
+  return OIT_OK;
+}
+
+int oit_buffer_size(const OitCtx* c, OitBuffer which, size_t* bytes)
+{
+  if(!c || !bytes)
+    return OIT_ERR_INVALID_ARG;
+  DevBuf* b = bufferOf(const_cast<OitCtx*>(c), which);
+  if(!b)
+    return OIT_ERR_INVALID_ARG;
+  *bytes = b->p ? b->bytes : 0;
+  return OIT_OK;
+}
+
+int oit_download(OitCtx* c, OitBuffer which, void* host, size_t bytes)
+{
+  if(!c || !host)
+    return OIT_ERR_INVALID_ARG;
+  DevBuf* b = bufferOf(c, which);
+  if(!b || !b->p)
+    return fail(c, OIT_ERR_INVALID_ARG, "buffer not allocated for this configuration");
+  if(bytes != b->bytes)
+    return fail(c, OIT_ERR_SIZE, "host size does not match the device buffer");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaMemcpyAsync(host, b->p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return OIT_OK;
+}
+
+int oit_upload(OitCtx* c, OitBuffer which, const void* host, size_t bytes)
+{
+  if(!c || !host)
+    return OIT_ERR_INVALID_ARG;
+  DevBuf* b = bufferOf(c, which);
+  if(!b || !b->p)
+    return fail(c, OIT_ERR_INVALID_ARG, "buffer not allocated for this configuration");
+  if(bytes != b->bytes)
+    return fail(c, OIT_ERR_SIZE, "host size does not match the device buffer");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaMemcpyAsync(b->p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return OIT_OK;
+}
+
+void* oit_device_ptr(OitCtx* c, OitBuffer which)
+{
+  if(!c)
+    return nullptr;
+  DevBuf* b = bufferOf(c, which);
+  return b ? b->p : nullptr;
+}
+
+int oit_read_color(OitCtx* c, void* bgra8, size_t bytes) { return oit_download(c, OIT_BUF_FINAL, bgra8, bytes); }
+
+void* oit_stream(OitCtx* c) { return c ? (void*)c->stream : nullptr; }
+
+int oit_local_row_to_global(const OitCtx* c, uint32_t localRow, uint32_t* globalRow)
+{
+  if(!c || !globalRow || localRow >= c->localOutH)
+    return OIT_ERR_INVALID_ARG;
+  const uint32_t strip = localRow / c->stripRows, within = localRow % c->stripRows;
+  *globalRow           = (strip * c->cfg.bandCount + c->cfg.bandIndex) * c->stripRows + within;
+  return OIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// oit_geometry.cu -- vertex stage, triangle setup / tile binning, and the small scan + stable radix sort they need.
+//
+// Replaces: object.vert.glsl:32-38 (K0), the fixed-function viewport transform and primitive assembly
+// (main.cpp:504-532) of the reference.  Output: per (local) screen tile, the list of triangles whose sample
+// bounding box touches it, IN PRIMITIVE ORDER -- the order the ROP and the ordered interlock rely on.
+#include "oit_device.cuh"
+
+namespace oit {
+
+// ------------------------------------------------------------------------------------------------------------------
+// vertex stage
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
+{
+  const float hw = 0.5f * (float)p.W, hh = 0.5f * (float)p.H;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nVerts; i += gridDim.x * blockDim.x)
+  {
+    const float* v  = p.verts + (size_t)i * 10;
+    const float  px = v[0], py = v[1], pz = v[2];
+    float        clip[4];
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+      clip[r] = __fmaf_rn(p.projView[0 + r], px, __fmaf_rn(p.projView[4 + r], py, __fmaf_rn(p.projView[8 + r], pz, p.projView[12 + r])));
+    TVert t;
+    t.viewz = __fmaf_rn(p.view[2], px, __fmaf_rn(p.view[6], py, __fmaf_rn(p.view[10], pz, p.view[14])));
+    t.x     = INT32_MIN;
+    t.y     = 0;
+    t.z     = 0.f;
+    t.invw  = 0.f;
+    if(clip[3] > 0.f && clip[3] < __int_as_float(0x7f800000))
+    {
+      const float invw = __fdiv_rn(1.0f, clip[3]);
+      const float nx = __fmul_rn(clip[0], invw), ny = __fmul_rn(clip[1], invw), nz = __fmul_rn(clip[2], invw);
+      const float xs = __fmaf_rn(nx, hw, hw), ys = __fmaf_rn(ny, hh, hh);
+      if(fabsf(xs) < GUARD_BAND_PX && fabsf(ys) < GUARD_BAND_PX && nz >= 0.f && nz <= 1.f)
+      {
+        t.x    = __float2int_rn(__fmul_rn(xs, 256.0f));
+        t.y    = __float2int_rn(__fmul_rn(ys, 256.0f));
+        t.z    = nz;
+        t.invw = invw;
+      }
+    }
+    p.tv[i] = t;
+  }
+}
+
+int launchTransformVertices(const FrameParams& p, cudaStream_t s)
+{
+  if(p.nVerts == 0)
+    return 0;
+  const int blocks = (int)min((p.nVerts + 255u) / 256u, 148u * 16u);
+  k_transform_vertices<<<blocks, 256, 0, s>>>(p);
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// triangle -> tile range
+// ------------------------------------------------------------------------------------------------------------------
+struct TileRange
+{
+  int tx0, tx1, ty0, ty1;  // global tile coordinates, inclusive; empty if tx0 > tx1
+};
+
+// The pixel range that can contain a covered sample: a sample of pixel px lies at px*256 + off, off in [lo, hi].
+__device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri, bool cullBack, TileRange& r)
+{
+  const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
+  const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
+  if(a.x == INT32_MIN || b.x == INT32_MIN || c.x == INT32_MIN)
+    return false;
+  const long long area2 = (long long)(b.x - a.x) * (c.y - a.y) - (long long)(c.x - a.x) * (b.y - a.y);
+  if(area2 == 0 || (cullBack && area2 > 0))
+    return false;
+  const int lo = p.msaa == 1 ? 128 : (p.msaa == 4 ? 32 : 16), hi = 256 - lo;
+  const int minx = min(a.x, min(b.x, c.x)), maxx = max(a.x, max(b.x, c.x));
+  const int miny = min(a.y, min(b.y, c.y)), maxy = max(a.y, max(b.y, c.y));
+  const int px0 = max((minx - hi + 255) >> 8, 0), px1 = min((maxx - lo) >> 8, p.W - 1);
+  const int py0 = max((miny - hi + 255) >> 8, 0), py1 = min((maxy - lo) >> 8, p.H - 1);
+  if(px0 > px1 || py0 > py1)
+    return false;
+  r.tx0 = px0 >> TILE_SHIFT;
+  r.tx1 = px1 >> TILE_SHIFT;
+  r.ty0 = py0 >> TILE_SHIFT;
+  r.ty1 = py1 >> TILE_SHIFT;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
+                                                   uint32_t* __restrict__ counts)
+{
+  unsigned long long rejected = 0;
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+  {
+    TileRange r;
+    uint32_t  n = 0;
+    if(triTileRange(p, firstTri + t, cullBack != 0, r))
+    {
+      const int nx = r.tx1 - r.tx0 + 1;
+      for(int R = r.ty0; R <= r.ty1; R++)
+        if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
+          n += nx;
+    }
+    else
+    {
+      const uint32_t* ix = p.indices + 3 * (size_t)(firstTri + t);
+      if(p.tv[ix[0]].x == INT32_MIN || p.tv[ix[1]].x == INT32_MIN || p.tv[ix[2]].x == INT32_MIN)
+        rejected++;
+    }
+    counts[t] = n;
+  }
+  if(rejected)
+    atomicAdd(&p.stats[STAT_REJECTED], rejected);
+}
+
+__global__ void __launch_bounds__(256) k_bin_emit(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
+                                                  const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ vals)
+{
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+  {
+    const uint32_t o0 = offsets[t], o1 = offsets[t + 1];
+    if(o0 == o1)
+      continue;
+    TileRange r;
+    triTileRange(p, firstTri + t, cullBack != 0, r);
+    uint32_t o = o0;
+    for(int R = r.ty0; R <= r.ty1; R++)
+      if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
+      {
+        const uint32_t rowKey = (uint32_t)tileRowToLocal(R, p.stripTileRows, p.bandCount) * p.tilesX;
+        for(int tx = r.tx0; tx <= r.tx1; tx++, o++)
+        {
+          keys[o] = rowKey + tx;
+          vals[o] = firstTri + t;
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (three kernels; the middle one is a single CTA walking the block sums)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS   = 8;
+constexpr int SCAN_TILE    = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums)
+{
+  __shared__ uint32_t sm[33];
+  const size_t        base = (size_t)blockIdx.x * SCAN_TILE;
+  uint32_t            acc  = 0;
+#pragma unroll
+  for(int k = 0; k < SCAN_ITEMS; k++)
+  {
+    const size_t i = base + (size_t)threadIdx.x * SCAN_ITEMS + k;
+    acc += i < n ? in[i] : 0u;
+  }
+  uint32_t total;
+  blockExclusiveScan(acc, sm, total);
+  if(threadIdx.x == 0)
+    sums[blockIdx.x] = total;
+}
+// in place: sums[i] <- exclusive prefix; sums[nb] <- grand total
+__global__ void __launch_bounds__(1024) k_scan_top(uint32_t* sums, size_t nb)
+{
+  __shared__ uint32_t sm[33];
+  uint32_t            carry = 0;
+  for(size_t base = 0; base < nb; base += blockDim.x)
+  {
+    const size_t   i = base + threadIdx.x;
+    const uint32_t v = i < nb ? sums[i] : 0u;
+    uint32_t       total;
+    const uint32_t ex = blockExclusiveScan(v, sm, total);
+    if(i < nb)
+      sums[i] = carry + ex;
+    carry += total;
+  }
+  if(threadIdx.x == 0)
+    sums[nb] = carry;
+}
+// out[i] = exclusive prefix of in (may alias); out[n] = grand total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* in, size_t n, const uint32_t* __restrict__ sums,
+                                                             uint32_t* out, size_t nb)
+{
+  __shared__ uint32_t sm[33];
+  const size_t        base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t            v[SCAN_ITEMS];
+  uint32_t            acc = 0;
+#pragma unroll
+  for(int k = 0; k < SCAN_ITEMS; k++)
+  {
+    v[k] = base + k < n ? in[base + k] : 0u;
+    acc += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = blockExclusiveScan(acc, sm, total) + sums[blockIdx.x];
+#pragma unroll
+  for(int k = 0; k < SCAN_ITEMS; k++)
+  {
+    if(base + k < n)
+      out[base + k] = ex;
+    ex += v[k];
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    out[n] = sums[nb];
+}
+
+static size_t scanBlocks(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+// exclusive scan of in[0..n) into out[0..n], out[n] = total. scratch: scanBlocks(n) + 1 words
+static int launchScan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch, cudaStream_t s)
+{
+  const size_t nb = scanBlocks(n);
+  if(nb == 0)
+  {
+    cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
+    return 0;
+  }
+  k_scan_sums<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, scratch);
+  k_scan_top<<<1, 1024, 0, s>>>(scratch, nb);
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, scratch, out, nb);
+  return 3;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key, value) pairs on 8-bit digits
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ROUNDS  = 16;
+constexpr int SORT_TILE    = SORT_THREADS * SORT_ROUNDS;
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, size_t n, int shift,
+                                                            uint32_t* __restrict__ table, uint32_t nb)
+{
+  __shared__ uint32_t hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+  for(int r = 0; r < SORT_ROUNDS; r++)
+  {
+    const size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
+    if(i < n)
+      atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  table[(size_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
+                                                               uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, size_t n,
+                                                               int shift, const uint32_t* __restrict__ table, uint32_t nb)
+{
+  __shared__ uint32_t off[256];
+  __shared__ uint32_t cnt[SORT_THREADS / 32][256];
+  const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  off[threadIdx.x] = table[(size_t)threadIdx.x * nb + blockIdx.x];
+#pragma unroll
+  for(int w = 0; w < SORT_THREADS / 32; w++)
+    cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+  for(int r = 0; r < SORT_ROUNDS; r++)
+  {
+    const size_t   i      = base + (size_t)r * SORT_THREADS + threadIdx.x;
+    const bool     active = i < n;
+    const uint32_t key    = active ? keysIn[i] : 0u;
+    const uint32_t val    = active ? valsIn[i] : 0u;
+    const uint32_t d      = active ? ((key >> shift) & 255u) : 256u;
+    const uint32_t peers  = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank   = __popc(peers & ((1u << lane) - 1u));
+    if(active && rank == 0)
+      cnt[warp][d] = __popc(peers);
+    __syncthreads();
+    if(active)
+    {
+      uint32_t prefix = 0;
+      for(int w = 0; w < warp; w++)
+        prefix += cnt[w][d];
+      const uint32_t dst = off[d] + prefix + rank;
+      keysOut[dst]       = key;
+      valsOut[dst]       = val;
+    }
+    __syncthreads();
+    {
+      uint32_t total = 0;
+#pragma unroll
+      for(int w = 0; w < SORT_THREADS / 32; w++)
+      {
+        total += cnt[w][threadIdx.x];
+        cnt[w][threadIdx.x] = 0;
+      }
+      off[threadIdx.x] += total;
+    }
+    __syncthreads();
+  }
+}
+
+// tileStart[t] = index of the first pair whose key is >= t; tileStart[numTiles] = n
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ keys, uint32_t n, uint32_t numTiles,
+                                                     uint32_t* __restrict__ tileStart)
+{
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const uint32_t k    = keys[i];
+    const uint32_t prev = i == 0 ? 0u : keys[i - 1] + 1u;
+    for(uint32_t t = prev; t <= k; t++)
+      tileStart[t] = i;
+    if(i == n - 1)
+      for(uint32_t t = k + 1; t <= numTiles; t++)
+        tileStart[t] = n;
+  }
+}
+
+size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t /*numTiles*/)
+{
+  const size_t sortBlocks = (pairCapacity + SORT_TILE - 1) / SORT_TILE;
+  const size_t table      = 256 * sortBlocks + 1;
+  return scanBlocks(triCount) + 2 + table + scanBlocks(table) + 2;
+}
+
+int launchBinCount(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, cudaStream_t s)
+{
+  if(triCount == 0)
+  {
+    cudaMemsetAsync(b.counts, 0, sizeof(uint32_t), s);
+    return 0;
+  }
+  const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
+  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts);
+  return 1 + launchScan(b.counts, b.counts, triCount, b.scratch, s);
+}
+
+int launchBinEmitSort(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
+                      uint32_t pairTotal, int* sortedBuf, cudaStream_t s)
+{
+  const uint32_t numTiles = (uint32_t)p.tilesX * p.tileRowsLocal;
+  int            launches = 0;
+  *sortedBuf              = 0;
+  if(pairTotal == 0 || triCount == 0)
+  {
+    cudaMemsetAsync(b.tileStart, 0, sizeof(uint32_t) * (numTiles + 1), s);
+    return 0;
+  }
+  const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
+  k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairKey[0], b.pairVal[0]);
+  launches++;
+  int bits = 1;
+  while((1u << bits) < numTiles)
+    bits++;
+  const uint32_t nb        = (uint32_t)((pairTotal + SORT_TILE - 1) / SORT_TILE);
+  uint32_t*      table     = b.scratch + scanBlocks(triCount) + 2;
+  uint32_t*      tableScan = table + (size_t)256 * nb + 1;
+  int            cur       = 0;
+  for(int shift = 0; shift < bits; shift += 8)
+  {
+    k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], pairTotal, shift, table, nb);
+    launches += 1 + launchScan(table, table, (size_t)256 * nb, tableScan, s);
+    k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairVal[cur], b.pairKey[cur ^ 1], b.pairVal[cur ^ 1], pairTotal,
+                                               shift, table, nb);
+    launches++;
+    cur ^= 1;
+  }
+  const int rblocks = (int)min((pairTotal + 255u) / 256u, 148u * 16u);
+  k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], pairTotal, numTiles, b.tileStart);
+  launches++;
+  *sortedBuf = cur;
+  return launches;
+}
+
+}  // namespace oit

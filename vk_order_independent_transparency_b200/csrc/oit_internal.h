@@ -1,0 +1,132 @@
+// oit_internal.h -- structures shared by the host API and the CUDA translation units of liboit_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/oit_b200.h"
+
+namespace oit {
+
+// Screen tiles: one CTA owns one tile for a whole geometry pass, so every per-pixel structure (A-buffer slice,
+// aux words, colour and depth samples) is touched by exactly one SM and primitive order per pixel can be kept.
+constexpr int TILE_W      = 16;
+constexpr int TILE_H      = 16;
+constexpr int TILE_PIX    = TILE_W * TILE_H;
+constexpr int TILE_SHIFT  = 4;
+constexpr int RASTER_THREADS = 256;  // = triangles staged per chunk
+constexpr int SUBPIXEL_BITS  = 8;    // fixed-point snapping (NVIDIA and lavapipe use 8)
+constexpr float GUARD_BAND_PX = 2097152.0f;  // |x|,|y| < 2^21 px so every edge delta fits in 31 bits
+
+// raster kernel variants
+enum RasterPass
+{
+  PASS_SIMPLE = 0,
+  PASS_LINKEDLIST,
+  PASS_LOOP_COLOR,
+  PASS_LOOP64,
+  PASS_SPINLOCK,
+  PASS_INTERLOCK,
+  PASS_WEIGHTED,
+  PASS_LOOP_DEPTH,
+  PASS_OPAQUE,
+  NUM_RASTER_PASSES
+};
+
+// post-vertex-stage vertex: object.vert.glsl:32-38 + viewport transform, snapped to 1/256 px
+struct TVert
+{
+  int32_t x, y;   // x == INT32_MIN marks a vertex outside the clip volume / guard band
+  float   z;      // z_ndc = z_clip / w_clip
+  float   invw;
+  float   viewz;  // (viewMatrix * pos).z  (Interpolants.depth)
+};
+static_assert(sizeof(TVert) == 20, "TVert layout");
+
+enum StatSlot
+{
+  STAT_FRAGMENTS = 0,
+  STAT_STORED,
+  STAT_TAIL,
+  STAT_OPAQUE,
+  STAT_REJECTED,
+  STAT_PAIRS,
+  NUM_STAT_SLOTS = 8
+};
+
+struct FrameParams
+{
+  // render target (after supersample); W x H is the full frame, localH the rows this band owns
+  int      W, H, localH;
+  int      msaa, sampleShading, coverage;
+  int      L;
+  uint32_t capacity;  // linked list pool size in nodes (scene.linkedListAllocatedPerElement)
+  int      tailBlend;
+  int      layers;    // A-buffer / aux layers (msaa if sample shading)
+  uint32_t clearColor;  // (0.2,0.2,0.2,0.2) linear encoded to BGRA8 sRGB (oitRender.cpp:90)
+  // tiles
+  int tilesX, tileRowsGlobal, tileRowsLocal;
+  int stripTileRows, bandCount, bandIndex;
+  // UBO scalars
+  float alphaMin, alphaWidth;
+  float projView[16];
+  float view[16];
+  // buffers (device)
+  uint32_t*            abuf;
+  uint32_t*            aux;
+  uint32_t*            spin;
+  uint32_t*            adepth;
+  uint32_t*            counter;
+  uint32_t*            color;
+  float*               depth;  // nullptr when nothing opaque is drawn: every sample reads 1.0
+  uint16_t*            wacc;
+  uint16_t*            wrev;
+  uint32_t*            fin;
+  const float*         tables;  // [0,256): sRGB8 -> linear, [256,512): encode thresholds
+  unsigned long long*  stats;
+  // geometry
+  const float*    verts;
+  const uint32_t* indices;
+  TVert*          tv;
+  uint32_t        nVerts;
+  // binning of the current draw
+  const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order
+  const uint32_t* tileStart;  // [numLocalTiles + 1]
+};
+
+__host__ __device__ inline int tileRowOwner(int R, int stripTileRows, int bandCount) { return (R / stripTileRows) % bandCount; }
+__host__ __device__ inline int tileRowToLocal(int R, int stripTileRows, int bandCount)
+{
+  return (R / (stripTileRows * bandCount)) * stripTileRows + (R % stripTileRows);
+}
+__host__ __device__ inline int tileRowToGlobal(int r, int stripTileRows, int bandCount, int bandIndex)
+{
+  return ((r / stripTileRows) * bandCount + bandIndex) * stripTileRows + (r % stripTileRows);
+}
+
+// ---- launchers (each returns the number of kernels it launched) -------------------------------------------------
+int launchTransformVertices(const FrameParams& p, cudaStream_t s);
+// bins triangles [firstTri, firstTri+triCount) of the index buffer; cullBack for the opaque draw.
+// d_counts/d_offsets: triCount+1 words; returns pair total through *hTotal (synchronises the stream once).
+struct BinBuffers
+{
+  uint32_t* counts;      // [triCount + 1]
+  uint32_t* pairKey[2];  // [pairCapacity]
+  uint32_t* pairVal[2];
+  uint32_t* tileStart;   // [numLocalTiles + 1]
+  uint32_t* scratch;     // scan / histogram scratch
+  size_t    scratchWords;
+  size_t    pairCapacity;
+  size_t    triCapacity;
+};
+int launchBinCount(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
+                   cudaStream_t s);
+int launchBinEmitSort(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
+                      uint32_t pairTotal, int* sortedBuf, cudaStream_t s);
+size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
+
+int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);
+int launchRaster(const FrameParams& p, int pass, cudaStream_t s);
+int launchComposite(const FrameParams& p, int algorithm, cudaStream_t s);
+int launchResolve(const FrameParams& p, int supersample, int outW, int outLocalH, cudaStream_t s);
+
+}  // namespace oit
