@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- transparent fragments/s and ms/frame of the OIT hot path on N B200s (see BASELINE.json / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload headline|config1..config5] [--impl reference]
+
+A step = one frame of the hot path (vertex stage + binning, clears, colour pass(es), composite, resolve [, band gather]).
+`value` is measured with the scene resident in HBM; `e2e` is the same frame through the C ABI with HOST buffers
+(scene + UBO uploaded from pinned memory and the resolved frame read back, every step).  N>1 is sort-first split frame:
+every rank renders its interleaved row strips and ONE NCCL all-gather exchanges the resolved strips.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, State kwargs, description)
+    "headline": (3840, 2160, dict(algorithm=1, aaType=4), "default sphere scene (1024 spheres, subdiv 16), Linked List, OIT_LAYERS=8, N=10, 8x MSAA coverage masks, 3840x2160"),
+    "config1": (1280, 720, dict(algorithm=1), "default scene, Linked List, no AA, 1280x720"),
+    "config2": (1920, 1080, dict(algorithm=3), "default scene, Loop64 OIT_LAYERS=8, no AA, 1920x1080"),
+    "config3": (1920, 1080, dict(algorithm=4, aaType=2), "default scene, Spinlock, 4x MSAA per-sample, 1920x1080"),
+    "config4": (3840, 2160, dict(algorithm=6, aaType=4), "default scene, WBOIT, 8x MSAA, 3840x2160"),
+    "config5": (3840, 2160, dict(algorithm=1, numObjects=100000, linkedListAllocatedPerElement=128), "100k spheres, Linked List N=128, no AA, 3840x2160, split frame"),
+}
+TECH_TABLE = [(a, 0) for a in range(7)]  # per-technique table at 3840x2160, no AA, default parameters
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def algorithmic_bytes(oit, st, stats, W, H, nVerts, nIndices):
+    """SURVEY 8(d) per-unit figures x the units of one frame, per stage (DESIGN.md 'Roofline accounting')."""
+    S = st.msaa
+    ss = st.supersample
+    P = W * ss * H * ss
+    Pa = P * (S if st.sampleShading else 1)
+    Ps = P * S
+    L = st.oitLayers
+    cov = st.coverageShading()
+    E = 16 if cov else 8
+    F, Fst, Ftb = stats["fragments"], stats["fragmentsStored"], stats["fragmentsTail"]
+    cbar = S / 2 if (cov or (st.algorithm == oit.OIT_WEIGHTED and S > 1)) else 1  # mean covered samples of a tail / WBOIT fragment (estimate)
+    geom = 40 * nVerts + 4 * nIndices
+    a = st.algorithm
+    if a == oit.OIT_LINKEDLIST:
+        clear, color, comp = 4 * Pa, Fst * 24 + Ftb * 8 * cbar, 4 * Pa + 16 * Fst + 8 * Ps
+    elif a == oit.OIT_LOOP64:
+        clear, color, comp = 8 * L * Pa, F * 16 + Ftb * 8 * cbar, 8 * min(Fst, L * Pa) + 8 * Ps
+    elif a == oit.OIT_LOOP:
+        clear, color, comp = 4 * L * Pa, F * 8 + F * 8 + geom, 8 * Fst + 8 * Ps
+    elif a == oit.OIT_SIMPLE:
+        clear, color, comp = 4 * Pa, F * 8 + Fst * E, 4 * Pa + E * Fst + 8 * Ps
+    elif a in (oit.OIT_SPINLOCK, oit.OIT_INTERLOCK):
+        clear, color, comp = (12 if a == oit.OIT_SPINLOCK else 8) * Pa, F * 12 + Fst * E, 4 * Pa + E * min(Fst, L * Pa) + 8 * Ps
+    else:
+        clear, color, comp = 10 * Ps, F * cbar * 20, 10 * Ps + 8 * Ps
+    clear += 4 * Ps                      # colour clear (render-pass clear of m_colorImage)
+    color += geom
+    resolve = 4 * Ps + 4 * W * H
+    return {"clear": clear, "color": color, "composite": comp, "resolve": resolve}
+
+
+def run_ours(args):
+    import torch
+    import vk_order_independent_transparency_b200 as oit
+    from vk_order_independent_transparency_b200 import split_frame as SF
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, kw, desc = WORKLOADS[args.workload]
+    st = oit.State(**kw)
+    verts, idx, ipo = oit.generate_scene(st)
+    # pinned host copies (e2e leg) and the device-resident scene (value leg)
+    hverts = torch.from_numpy(verts).pin_memory()
+    hidx = torch.from_numpy(idx.view(np.int32)).pin_memory()
+    dverts, didx = hverts.to(dev), hidx.to(dev)
+    ubo = oit.default_camera(W, H)
+    s = oit.Sample(st, W, H, device=local, bandCount=world, bandIndex=rank, stripRows=args.strip_rows)
+    s.setSceneDevice(dverts.data_ptr(), verts.shape[0], didx.data_ptr(), idx.size, ipo, keepalive=(dverts, didx))
+    stream = torch.cuda.ExternalStream(s.L.oit_stream(s.h), device=dev)
+    fin_dev = torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
+    pad = SF.max_band_rows(H, world, args.strip_rows)
+    gather_buf = torch.empty((world, pad, W), dtype=torch.int32, device=dev)
+    hfinal = torch.empty((s.localRows, W), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        s.onRender(ubo)                      # synchronous: the strips of this band are complete on the device
+        if world > 1:
+            SF.gather_frame(fin_dev, H, W, rank, world, args.strip_rows, gather_buf=gather_buf)
+
+    def step_e2e():
+        s.setScene(hverts.numpy(), hidx.numpy().view(np.uint32), ipo)   # H2D of the step's inputs from pinned memory
+        s.onRender(ubo)
+        if world > 1:
+            SF.gather_frame(fin_dev, H, W, rank, world, args.strip_rows, gather_buf=gather_buf)
+        s.readColor(hfinal.numpy().view(np.uint32))                      # D2H of the step's result
+
+    def timed(step, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage = {"geometry": 0.0, "clear": 0.0, "color": 0.0, "composite": 0.0, "resolve": 0.0, "opaque": 0.0}
+        launches = 0
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+            sst = s.stats()
+            launches += sst["kernelLaunches"]
+            for k, n in (("geometry", "msGeometry"), ("clear", "msClear"), ("color", "msColor"), ("composite", "msComposite"), ("resolve", "msResolve"), ("opaque", "msOpaque")):
+                stage[k] += sst[n]
+        if world > 1:
+            torch.cuda.current_stream().synchronize()
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max(e0.elapsed_time(e1), 0.0)
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), {k: v / steps for k, v in stage.items()}, launches, clocks, sst
+
+    ms_total, wall_total, stage_ms, launches, clocks, last = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    F_local = last["fragments"]
+    Ft = torch.tensor([F_local, last["fragmentsStored"], last["fragmentsTail"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(Ft)
+    F, Fst, Ftb = (int(x) for x in Ft.tolist())
+    # with N>1 the all-gather runs on torch's stream after the synchronous render, so the wall clock of the loop (max over
+    # ranks, bracketed by barrier + synchronize) is the honest frame time; at N=1 device events and wall clock agree.
+    frame_ms = (wall_total if world > 1 else ms_total) / args.steps
+    e_ms_total, e_wall_total, _, _, _, _ = timed(step_e2e, max(3, args.steps // 2), 3)
+    e_steps = max(3, args.steps // 2)
+    e2e_ms = (e_wall_total if world > 1 else max(e_ms_total, e_wall_total)) / e_steps
+
+    peak, peak_src = peaks()
+    bytes_stage = algorithmic_bytes(oit, st, {"fragments": F_local, "fragmentsStored": last["fragmentsStored"], "fragmentsTail": last["fragmentsTail"]},
+                                    W, s.localRows, verts.shape[0], idx.size)
+    dom = max(("color", "composite", "clear", "resolve"), key=lambda k: stage_ms[k])
+    kernel_name = {"color": "k_raster (fragment insert)", "composite": "k_composite", "clear": "k_fill32", "resolve": "k_resolve"}[dom]
+    achieved = bytes_stage[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    frame_bytes = sum(bytes_stage.values())
+    per_stage = {k: {"ms": round(stage_ms[k], 4), "alg_bytes": int(bytes_stage.get(k, 0)),
+                     "gbs": round(bytes_stage.get(k, 0) / (stage_ms[k] * 1e-3) / 1e9, 1) if stage_ms[k] > 0 and k in bytes_stage else None}
+                 for k in stage_ms}
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "transparent fragments/s", "value": F / (frame_ms * 1e-3), "unit": "fragments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32/f32 (rgba8 + f32 depth A-buffer words, fp32 blend)",
+            "data": "synthetic (the sample's seeded sphere cloud, generated on the host)",
+            "config": {"workload": f"{args.workload}: {desc}", "fragments_per_frame": F, "fragments_stored": Fst, "fragments_tail": Ftb,
+                       "width": W, "height": H, "parallelism": f"split-frame x{world}, {args.strip_rows}-row interleaved strips" if world > 1 else "single GPU",
+                       "l2_policy": "working set (A-buffer + colour samples) is larger than L2; no explicit flush"},
+            "ms_per_frame": frame_ms, "stages": per_stage, "gpu_launches": int(launches),
+            "e2e": {"value": F / (e2e_ms * 1e-3), "unit": "fragments/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes + 224), "d2h_bytes_per_step": int(s.localRows * W * 4),
+                    "note": "scene (vertices + indices) and UBO uploaded from pinned host memory and the resolved strips read back every step"},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "stage": dom, "alg_bytes_per_launch": int(bytes_stage[dom]),
+                         "frame": {"alg_bytes": int(frame_bytes), "achieved": frame_bytes / (frame_ms * 1e-3) / 1e9,
+                                   "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak}},
+            "clocks": clocks,
+        }
+    # per-technique table @3840x2160 (the metric is quoted per technique), N=1 only
+    if rank == 0 and world == 1 and not args.no_table:
+        table = {}
+        for alg, aa in TECH_TABLE:
+            stt = oit.State(algorithm=alg, aaType=aa)
+            t = oit.Sample(stt, 3840, 2160, device=local)
+            t.setSceneDevice(dverts.data_ptr(), verts.shape[0], didx.data_ptr(), idx.size, ipo, keepalive=(dverts, didx))
+            for _ in range(3):
+                t.onRender(oit.default_camera(3840, 2160))
+            ms = []
+            for _ in range(5):
+                t.onRender(oit.default_camera(3840, 2160))
+                ms.append(t.stats()["msFrame"])
+            ts = t.stats()
+            table[oit.ALGORITHM_NAMES[alg]] = {"ms_per_frame": float(np.mean(ms)), "fragments": ts["fragments"],
+                                               "fragments_per_s": ts["fragments"] / (np.mean(ms) * 1e-3)}
+            t.close()
+        out["per_technique_4k_noaa"] = table
+    # CPU baseline: the oracle on this box's host cores, one frame of the same workload (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args.workload, 1, 0)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def cpu_baseline(workload, steps, warmup):
+    """The oracle (CPU restatement of the reference path; the reference itself needs Vulkan and cannot run here),
+    band-parallel over all host cores."""
+    from oracle import oracle_py as O
+    W, H, kw, desc = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    cfg = O.make_config(width=W, height=H, **kw)
+    bounded = ""
+    if kw.get("numObjects", 1024) > 20000:
+        cfg.numObjects = 20000  # bounded sample of config 5: the first 20k spheres
+        bounded = " (bounded sample: first 20000 spheres)"
+    verts, idx, ipo = O.generate_scene(cfg)
+    o = O.Oracle(cfg, threads=cores)
+    o.set_scene(verts, idx, ipo)
+    sd = O.camera(W, H)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        o.render(sd)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if sum(times) > 150:
+            break
+    F = o.stats["fragments"]
+    o.close()
+    t = float(np.mean(times))
+    return {"value": F / t, "unit": "fragments/s", "cores": cores, "kind": "port", "ms_per_frame": t * 1e3, "frames_timed": len(times),
+            "sample": f"{len(times)} full frame(s) of {workload}{bounded}, {F} fragments each, oracle/liboit_oracle.so with {cores} OpenMP threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.workload, args.steps, min(args.warmup, 1))
+    W, H, kw, desc = WORKLOADS[args.workload]
+    print(json.dumps({
+        "impl": "reference", "metric": "transparent fragments/s", "value": cb["value"], "unit": "fragments/s", "n_gpus": args.gpus,
+        "steps": cb["frames_timed"], "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic (the sample's seeded sphere cloud)",
+        "config": {"workload": f"{args.workload}: {desc}", "note": "the reference's Vulkan path cannot run here (no Vulkan loader/ICD, nvpro_core2, shaderc); "
+                   "this arm is its CPU restatement (the oracle) on the host cores"},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--strip-rows", type=int, default=32)
+    ap.add_argument("--no-table", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
