@@ -663,10 +663,11 @@ struct Bary
 };
 inline Bary baryAt(const Tri& t, int64_t px, int64_t py)
 {
-  const float fa = (float)t.area2;
+  /* screen-space barycentrics: edge function times the reciprocal of the doubled area (one IEEE division per triangle) */
+  const float ra = 1.0f / (float)t.area2;
   Bary        b;
-  b.l1 = (float)edgeFn(t, 1, px, py) / fa;
-  b.l2 = (float)edgeFn(t, 2, px, py) / fa;
+  b.l1 = (float)edgeFn(t, 1, px, py) * ra;
+  b.l2 = (float)edgeFn(t, 2, px, py) * ra;
   b.l0 = (1.0f - b.l1) - b.l2;
   return b;
 }

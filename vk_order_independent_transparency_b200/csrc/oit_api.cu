@@ -25,6 +25,8 @@ void buildTables(float* t)
   t[256] = -std::numeric_limits<float>::infinity();
   for(int k = 1; k < 256; k++)
     t[256 + k] = (float)srgbToLinearD((k - 0.5) / 255.0);
+  for(int v = 0; v < 256; v++)
+    t[512 + v] = (float)v / 255.0f;
 }
 uint32_t hostEnc8(const float* t, float c)
 {
@@ -435,9 +437,9 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   if(cfg->percentTransparent < 100)
     CREATE_TRY(devAlloc(c, c->depth, P * c->msaa * 4));
   CREATE_TRY(devAlloc(c, c->fin, std::max<size_t>((size_t)cfg->width * c->localOutH, 1) * 4));
-  CREATE_TRY(devAlloc(c, c->tables, 512 * sizeof(float)));
+  CREATE_TRY(devAlloc(c, c->tables, 768 * sizeof(float)));
   CREATE_TRY(devAlloc(c, c->stats, NUM_STAT_SLOTS * sizeof(unsigned long long)));
-  float tables[512];
+  float tables[768];
   buildTables(tables);
   CREATE_CUDA(cudaMemcpy(c->tables.p, tables, sizeof(tables), cudaMemcpyHostToDevice));
   CREATE_CUDA(cudaMemset(c->stats.p, 0, c->stats.bytes));

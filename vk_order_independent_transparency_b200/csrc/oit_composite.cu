@@ -141,7 +141,35 @@ template <int LMAX, int COV>
 __device__ __forceinline__ Color4 blendSorted(const SrgbTables& t, const Elem (&a)[LMAX], int n)
 {
   Color4 sum = zeroColor();
-  if(COV > 1)
+  if(COV > 1 && LMAX <= 16)
+  {
+    // unpack + premultiply every fragment once (doBlendPacked is a pure function of the packed word), then run the
+    // per-sample coverage loops on registers
+    Color4 pm[LMAX];
+#pragma unroll
+    for(int i = 0; i < LMAX; i++)
+      if(i < n)
+        pm[i] = premultiply(unpackColor(t, a[i].c));
+#pragma unroll 1
+    for(int s = 0; s < COV; s++)
+    {
+      Color4 sc = zeroColor();
+#pragma unroll
+      for(int i = 0; i < LMAX; i++)
+        if(i < n && (a[i].m & (1u << s)))
+          doBlend(sc, pm[i]);
+      sum.r = __fadd_rn(sum.r, sc.r);
+      sum.g = __fadd_rn(sum.g, sc.g);
+      sum.b = __fadd_rn(sum.b, sc.b);
+      sum.a = __fadd_rn(sum.a, sc.a);
+    }
+    const float inv = 1.0f / (float)COV;
+    sum.r           = __fmul_rn(sum.r, inv);
+    sum.g           = __fmul_rn(sum.g, inv);
+    sum.b           = __fmul_rn(sum.b, inv);
+    sum.a           = __fmul_rn(sum.a, inv);
+  }
+  else if(COV > 1)
   {
 #pragma unroll 1
     for(int s = 0; s < COV; s++)
@@ -182,8 +210,21 @@ __device__ __forceinline__ void ropComposite(const FrameParams& p, const SrgbTab
   if(perSample)
     px[sampleID] = ropPremult(t, px[sampleID], out);
   else
-    for(int s = 0; s < p.msaa; s++)
-      px[s] = ropPremult(t, px[s], out);
+  {
+    // the blend is a pure function of (dst, src): samples holding the same destination word share one evaluation
+    uint32_t prevDst = px[0], prevRes = ropPremult(t, prevDst, out);
+    px[0]            = prevRes;
+    for(int s = 1; s < p.msaa; s++)
+    {
+      const uint32_t d = px[s];
+      if(d != prevDst)
+      {
+        prevDst = d;
+        prevRes = ropPremult(t, d, out);
+      }
+      px[s] = prevRes;
+    }
+  }
 }
 
 // KIND 0: fixed-slot k-buffer (Simple / Spinlock / Interlock); KIND 1: linked list

@@ -15,28 +15,31 @@ struct SrgbTables
 {
   float dec[256];  // sRGB8 code -> linear
   float thr[256];  // thr[k]: smallest linear value whose code is >= k; thr[0] = -inf
+  float a255[256]; // v / 255.0f
 };
 
 __device__ __forceinline__ void loadTables(SrgbTables& sm, const float* __restrict__ g)
 {
-  for(int i = threadIdx.x; i < 512; i += blockDim.x)
+  for(int i = threadIdx.x; i < 768; i += blockDim.x)
     reinterpret_cast<float*>(&sm)[i] = g[i];
 }
 
 __device__ __forceinline__ float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
-// 8-bit sRGB code of a linear value: number of thresholds <= c (branch-free binary search)
+// 8-bit sRGB code of a linear value = the largest k with c >= thr[k].  A guess from the closed form (fast, inexact
+// intrinsics) is made EXACT by walking the threshold table, so the result does not depend on the guess.
 __device__ __forceinline__ uint32_t enc8(const SrgbTables& t, float c)
 {
-  uint32_t k = 0;
-#pragma unroll
-  for(uint32_t step = 128; step; step >>= 1)
-    if(c >= t.thr[k + step])
-      k += step;
-  return k;
+  const float cc = fminf(fmaxf(c, 0.f), 1.f);
+  const float s  = cc < 0.0031308f ? 12.92f * cc : 1.055f * __powf(cc, 0.41666666f) - 0.055f;
+  int         k  = min(max(__float2int_rn(s * 255.0f), 0), 255);
+  while(k > 0 && c < t.thr[k])
+    k--;
+  while(k < 255 && c >= t.thr[k + 1])
+    k++;
+  return (uint32_t)k;
 }
 __device__ __forceinline__ uint32_t unorm8(float a) { return __float2uint_rn(__fmul_rn(clamp01(a), 255.0f)); }
-__device__ __forceinline__ float    a255(uint32_t v) { return __fdiv_rn((float)v, 255.0f); }
 
 struct Color4
 {
@@ -53,7 +56,7 @@ __device__ __forceinline__ uint32_t packColor(const SrgbTables& t, const Color4&
 // unPremultSRGBToLinear(unpackUnorm4x8(p)) (shaderCommon.glsl:84-104)
 __device__ __forceinline__ Color4 unpackColor(const SrgbTables& t, uint32_t p)
 {
-  return Color4{t.dec[p & 255], t.dec[(p >> 8) & 255], t.dec[(p >> 16) & 255], a255(p >> 24)};
+  return Color4{t.dec[p & 255], t.dec[(p >> 8) & 255], t.dec[(p >> 16) & 255], t.a255[p >> 24]};
 }
 __device__ __forceinline__ Color4 premultiply(const Color4& c)
 {
@@ -77,7 +80,7 @@ __device__ __forceinline__ void doBlendPacked(const SrgbTables& t, Color4& color
 // ---- ROP on the B8G8R8A8_SRGB colour target (oit.cpp:58; blend states main.cpp:540-592) ----------------------------
 __device__ __forceinline__ Color4 decodeDst(const SrgbTables& t, uint32_t d)
 {
-  return Color4{t.dec[(d >> 16) & 255], t.dec[(d >> 8) & 255], t.dec[d & 255], a255(d >> 24)};
+  return Color4{t.dec[(d >> 16) & 255], t.dec[(d >> 8) & 255], t.dec[d & 255], t.a255[d >> 24]};
 }
 __device__ __forceinline__ uint32_t encodeDst(const SrgbTables& t, const Color4& c)
 {

@@ -1,0 +1,412 @@
+// oit_fragment.cuh -- triangle slot, varyings/shading and the per-technique fragment ("colour pass") programs.
+// Included by oit_raster.cu only.  Reference citations are on each function.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "oit_device.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace oit {
+
+struct TriSlot
+{
+  int32_t  x[3], y[3];    // snapped vertex positions, re-ordered so that area2 > 0
+  float    z0, dz1, dz2;  // screen-linear depth plane through vertex 0
+  float    iw[3];
+  uint32_t vidx[3];
+  float    rarea;         // 1 / (float)area2
+  uint32_t box;           // bx0 | by0 << 4 | (bw-1) << 8 | (bh-1) << 12 | bias bits << 16 | zSafe << 19 | small << 20
+  uint32_t rcpW;          // ceil(65536 / bw)
+};
+
+struct FragCtx
+{
+  const FrameParams& p;
+  const SrgbTables&  t;
+  uint32_t           nFrag, nStored, nTail, nOpaque;
+};
+
+__device__ __forceinline__ uint32_t ldcg32(const uint32_t* a) { return __ldcg(a); }
+__device__ __forceinline__ unsigned long long ldcg64(const unsigned long long* a) { return __ldcg(a); }
+
+// ---- varyings + shading -------------------------------------------------------------------------------------------
+struct Bary
+{
+  float l0, l1, l2;
+};
+// screen-space barycentrics from the (unbiased) edge functions 1 and 2, already converted to float
+__device__ __forceinline__ Bary makeBary(float e1, float e2, float rarea)
+{
+  Bary b;
+  b.l1 = __fmul_rn(e1, rarea);
+  b.l2 = __fmul_rn(e2, rarea);
+  b.l0 = __fsub_rn(__fsub_rn(1.0f, b.l1), b.l2);
+  return b;
+}
+__device__ __forceinline__ float depthAt(const TriSlot& s, const Bary& b)
+{
+  return clamp01(__fmaf_rn(b.l2, s.dz2, __fmaf_rn(b.l1, s.dz1, s.z0)));
+}
+
+// Interpolants (shaderCommon.glsl:25-31) perspective-correct at `b`, then shading() (shaderCommon.glsl:36-56)
+template <bool NEED_VIEWZ>
+__device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s, const Bary& b, float& viewz)
+{
+  const float q0 = __fmul_rn(b.l0, s.iw[0]), q1 = __fmul_rn(b.l1, s.iw[1]), q2 = __fmul_rn(b.l2, s.iw[2]);
+  const float rden = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(q0, q1), q2));
+  const float* a0 = p.verts + (size_t)s.vidx[0] * 10;
+  const float* a1 = p.verts + (size_t)s.vidx[1] * 10;
+  const float* a2 = p.verts + (size_t)s.vidx[2] * 10;
+  float        v[7];
+#pragma unroll
+  for(int k = 0; k < 7; k++)
+    v[k] = __fmul_rn(__fmaf_rn(q2, __ldg(a2 + 3 + k), __fmaf_rn(q1, __ldg(a1 + 3 + k), __fmul_rn(q0, __ldg(a0 + 3 + k)))), rden);
+  if(NEED_VIEWZ)
+    viewz = __fmul_rn(__fmaf_rn(q2, p.tv[s.vidx[2]].viewz, __fmaf_rn(q1, p.tv[s.vidx[1]].viewz, __fmul_rn(q0, p.tv[s.vidx[0]].viewz))), rden);
+  const float LX = -0.40824829046386301637f, LY = 0.81649658092772603273f, LZ = 0.40824829046386301637f;
+  const float len2 = __fmaf_rn(v[2], v[2], __fmaf_rn(v[1], v[1], __fmul_rn(v[0], v[0])));
+  float       nx = 0.f, ny = 0.f, nz = 0.f;
+  if(len2 > 0.f)
+  {
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+    nx              = __fmul_rn(v[0], inv);
+    ny              = __fmul_rn(v[1], inv);
+    nz              = __fmul_rn(v[2], inv);
+  }
+  const float d      = __fmaf_rn(nz, LZ, __fmaf_rn(ny, LY, __fmul_rn(nx, LX)));
+  const float warmth = __fmaf_rn(d, 0.5f, 0.5f);
+  const float om     = __fsub_rn(1.0f, warmth);
+  Color4      c;
+  c.r = __fmul_rn(v[3], __fmaf_rn(0.0f, om, warmth));
+  c.g = __fmul_rn(v[4], __fmaf_rn(0.25f, om, warmth));
+  c.b = __fmul_rn(v[5], __fmaf_rn(0.75f, om, warmth));
+  c.a = clamp01(__fmaf_rn(v[6], p.alphaWidth, p.alphaMin));
+  return c;
+}
+
+// ---- fragment programs ----------------------------------------------------------------------------------------------
+// All return the colour handed to the ROP (premultiplied; zero = no-op).  x, yl: pixel (yl = row inside this band's
+// buffers); pix = yl * W + x; ai = aux index of (sampleID, pixel).
+
+// K2 oitSimple.frag.glsl:50-91
+__device__ __forceinline__ Color4 fragSimple(FragCtx& c, size_t pix, size_t ai, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z)
+{
+  const FrameParams& p        = c.p;
+  const size_t       viewSize = (size_t)p.W * p.localH;
+  const size_t       listPos  = viewSize * p.L * sampleID + pix;
+  const uint32_t     old      = atomicAdd(&p.aux[ai], 1u);
+  if(old < (uint32_t)p.L)
+  {
+    const uint32_t packed = packColor(c.t, rgba);
+    if(p.coverage)
+      reinterpret_cast<uint4*>(p.abuf)[listPos + (size_t)old * viewSize] = make_uint4(packed, __float_as_uint(z), mask, 0u);
+    else
+      reinterpret_cast<uint2*>(p.abuf)[listPos + (size_t)old * viewSize] = make_uint2(packed, __float_as_uint(z));
+    c.nStored++;
+    return zeroColor();
+  }
+  if(p.tailBlend)
+  {
+    c.nTail++;
+    return premultiply(rgba);
+  }
+  return zeroColor();
+}
+
+// K4 oitLinkedList.frag.glsl:51-85 -- the single-address counter is bumped once per converged warp group
+__device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t mask, const Color4& rgba, float z)
+{
+  const FrameParams& p = c.p;
+  uint32_t           newOffset;
+  {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t            base = 0;
+    if(g.thread_rank() == 0)
+      base = atomicAdd(p.counter, g.size());
+    newOffset = g.shfl(base, 0) + g.thread_rank() + 1u;
+  }
+  if(newOffset >= p.capacity)
+  {
+    if(p.tailBlend)
+    {
+      c.nTail++;
+      return premultiply(rgba);
+    }
+    return zeroColor();
+  }
+  const uint32_t oldOffset = atomicExch(&p.aux[ai], newOffset);
+  reinterpret_cast<uint4*>(p.abuf)[newOffset] =
+      make_uint4(packColor(c.t, rgba), __float_as_uint(z), p.coverage ? mask : 0u, oldOffset);
+  c.nStored++;
+  return zeroColor();
+}
+
+// K6 oitLoop.frag.glsl:57-100 (depth pass)
+__device__ __forceinline__ void fragLoopDepth(FragCtx& c, size_t pix, uint32_t sampleID, float z)
+{
+  const FrameParams& p        = c.p;
+  const size_t       viewSize = (size_t)p.W * p.localH;
+  uint32_t*          list     = p.abuf + viewSize * p.L * 2 * sampleID + pix;
+  uint32_t           zcur     = __float_as_uint(z);
+  int                i        = 0;
+  uint32_t           pretest  = ldcg32(list + (size_t)(p.L - 1) * viewSize);
+  if(zcur > pretest)
+    return;
+  pretest = ldcg32(list + (size_t)(p.L / 2) * viewSize);
+  if(zcur > pretest)
+    i = p.L / 2;
+  for(; i < p.L; i++)
+  {
+    const uint32_t ztest = atomicMin(list + (size_t)i * viewSize, zcur);
+    if(ztest == 0xFFFFFFFFu || ztest == zcur)
+      break;
+    zcur = max(ztest, zcur);
+  }
+}
+// K7 oitLoop.frag.glsl:120-173 (colour pass)
+__device__ __forceinline__ Color4 fragLoopColor(FragCtx& c, size_t pix, uint32_t sampleID, const Color4& rgba, float z)
+{
+  const FrameParams& p        = c.p;
+  const size_t       viewSize = (size_t)p.W * p.localH;
+  uint32_t*          list     = p.abuf + viewSize * p.L * 2 * sampleID + pix;
+  const uint32_t     zcur     = __float_as_uint(z);
+  if(list[(size_t)(p.L - 1) * viewSize] < zcur)
+  {
+    if(p.tailBlend)
+    {
+      c.nTail++;
+      return premultiply(rgba);
+    }
+    return zeroColor();
+  }
+  int start = 0, end = p.L - 1;
+  while(start < end)
+  {
+    const int      mid   = (start + end) / 2;
+    const uint32_t ztest = list[(size_t)mid * viewSize];
+    if(ztest < zcur)
+      start = mid + 1;
+    else
+      end = mid;
+  }
+  list[(size_t)(p.L + start) * viewSize] = packColor(c.t, rgba);
+  c.nStored++;
+  return zeroColor();
+}
+
+// K9 oitLoop64.frag.glsl:65-141: key = depth << 32 | rgba8, cascade of 64-bit atomicMin
+__device__ __forceinline__ Color4 fragLoop64(FragCtx& c, size_t pix, uint32_t sampleID, const Color4& rgba, float z)
+{
+  const FrameParams&  p        = c.p;
+  const size_t        viewSize = (size_t)p.W * p.localH;
+  unsigned long long* list     = reinterpret_cast<unsigned long long*>(p.abuf) + viewSize * p.L * sampleID + pix;
+  unsigned long long  zcur     = ((unsigned long long)__float_as_uint(z) << 32) | packColor(c.t, rgba);
+  int                 i        = 0;
+  bool                canInsert = true;
+  unsigned long long  pretest   = ldcg64(list + (size_t)(p.L - 1) * viewSize);
+  if(zcur > pretest)
+    canInsert = false;
+  else
+  {
+    pretest = ldcg64(list + (size_t)(p.L / 2) * viewSize);
+    if(zcur > pretest)
+      i = p.L / 2;
+  }
+  bool evict = true;
+  if(canInsert)
+  {
+    for(; i < p.L; i++)
+    {
+      const unsigned long long ztest = atomicMin(list + (size_t)i * viewSize, zcur);
+      if(ztest == ~0ull)
+      {
+        evict = false;
+        break;
+      }
+      zcur = ztest > zcur ? ztest : zcur;
+    }
+  }
+  if(!evict)
+  {
+    c.nStored++;
+    return zeroColor();
+  }
+  if(p.tailBlend)
+  {
+    c.nTail++;
+    return premultiply(unpackColor(c.t, (uint32_t)(zcur & 0xFFFFFFFFull)));
+  }
+  return zeroColor();
+}
+
+// the critical section shared by K11 (oitSpinlock.frag.glsl:86-118) and K13 (oitInterlock.frag.glsl:110-145).
+// Runs with the pixel exclusively owned (tile-ordered arbitration), so plain loads / stores are sufficient.
+__device__ __forceinline__ bool lockCriticalSection(FragCtx& c, size_t pix, size_t ai, uint32_t sampleID, uint32_t mask, uint32_t packed,
+                                                    uint32_t zbits, Color4& color)
+{
+  const FrameParams& p        = c.p;
+  const size_t       viewSize = (size_t)p.W * p.localH;
+  const size_t       listPos  = viewSize * p.L * sampleID + pix;
+  const uint32_t     oldCounter = p.aux[ai];
+  p.aux[ai]                     = oldCounter + 1u;
+  if(oldCounter < (uint32_t)p.L)
+  {
+    if(p.coverage)
+      reinterpret_cast<uint4*>(p.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint4(packed, zbits, mask, 0u);
+    else
+      reinterpret_cast<uint2*>(p.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint2(packed, zbits);
+    color = zeroColor();
+    return true;
+  }
+  int      furthest = 0;
+  uint32_t maxDepth = 0;
+  for(int i = 0; i < p.L; i++)
+  {
+    const size_t   e         = listPos + (size_t)i * viewSize;
+    const uint32_t testDepth = p.coverage ? p.abuf[e * 4 + 1] : p.abuf[e * 2 + 1];
+    if(testDepth > maxDepth)
+    {
+      maxDepth = testDepth;
+      furthest = i;
+    }
+  }
+  if(maxDepth > zbits)
+  {
+    const size_t e = listPos + (size_t)furthest * viewSize;
+    if(p.coverage)
+    {
+      color                               = unpackColor(c.t, p.abuf[e * 4]);
+      reinterpret_cast<uint4*>(p.abuf)[e] = make_uint4(packed, zbits, mask, 0u);
+    }
+    else
+    {
+      color                               = unpackColor(c.t, p.abuf[e * 2]);
+      reinterpret_cast<uint2*>(p.abuf)[e] = make_uint2(packed, zbits);
+    }
+    p.adepth[ai] = maxDepth;
+    return true;
+  }
+  return false;
+}
+
+// K11 oitSpinlock.frag.glsl:49-129 (keeps the reference's lock protocol: exchange-acquire, exchange-release, and the
+// while(!done) shape that is deadlock-free under independent thread scheduling) and K13 oitInterlock.frag.glsl:90-152
+template <bool SPIN>
+__device__ __forceinline__ Color4 fragLock(FragCtx& c, size_t pix, size_t ai, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z)
+{
+  const FrameParams& p      = c.p;
+  const uint32_t     zbits  = __float_as_uint(z);
+  const uint32_t     packed = packColor(c.t, rgba);
+  Color4             color  = rgba;
+  bool               stored = false;
+  if(SPIN)
+  {
+    const uint32_t oldDepth = ldcg32(&p.adepth[ai]);  // racy-but-conservative early-out outside the lock (:67-68)
+    if(zbits <= oldDepth)
+    {
+      bool done = mask == 0;
+      while(!done)
+      {
+        const uint32_t old = atomicExch(&p.spin[ai], 1u);
+        if(old == 0u)
+        {
+          stored = lockCriticalSection(c, pix, ai, sampleID, mask, packed, zbits, color);
+          __threadfence();
+          atomicExch(&p.spin[ai], 0u);
+          done = true;
+        }
+      }
+    }
+  }
+  else
+  {
+    // beginInvocationInterlock .. endInvocationInterlock: the arbitration loop of the caller IS the ordered interlock
+    if(zbits <= p.adepth[ai])
+      stored = lockCriticalSection(c, pix, ai, sampleID, mask, packed, zbits, color);
+  }
+  if(stored)
+    c.nStored++;
+  if(!p.tailBlend)
+    return zeroColor();  // outColor never written in the reference (oitSpinlock.frag.glsl:126-128): defined as 0
+  const Color4 out = premultiply(color);
+  if(!isZero(out))
+    c.nTail++;
+  return out;
+}
+
+// K15 oitWeighted.frag.glsl:53-79 + BlendMode::WEIGHTED_COLOR into RGBA16F / R16F (main.cpp:559-575)
+template <int S>
+__device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, uint32_t mask, const Color4& rgba, float viewz)
+{
+  const FrameParams& p   = c.p;
+  const Color4       col = premultiply(rgba);
+  const float        depthZ = __fmul_rn(-viewz, 10.0f);
+  const float        x      = __fdiv_rn(depthZ, 200.0f);
+  const float        x2     = __fmul_rn(x, x);
+  const float        x4     = __fmul_rn(x2, x2);
+  float              distWeight = __fdiv_rn(0.03f, __fadd_rn(1e-5f, x4));
+  distWeight                    = distWeight < 1e-2f ? 1e-2f : (distWeight > 3e3f ? 3e3f : distWeight);
+  const float mx     = fmaxf(fmaxf(col.r, col.g), fmaxf(col.b, col.a));
+  float       aw     = fminf(1.0f, __fmaf_rn(mx, 40.0f, 0.01f));
+  aw                 = __fmul_rn(aw, aw);
+  const float weight = __fmul_rn(aw, distWeight);
+  const float om     = __fsub_rn(1.0f, col.a);
+  const float src[4] = {__fmul_rn(col.r, weight), __fmul_rn(col.g, weight), __fmul_rn(col.b, weight), __fmul_rn(col.a, weight)};
+  uint16_t*   acc    = p.wacc + pix * S * 4;
+  uint16_t*   rev    = p.wrev + pix * S;
+#pragma unroll
+  for(int s = 0; s < S; s++)
+    if(mask & (1u << s))
+    {
+      ushort4 a = reinterpret_cast<ushort4*>(acc)[s];
+      a.x       = f2h(__fadd_rn(h2f(a.x), src[0]));
+      a.y       = f2h(__fadd_rn(h2f(a.y), src[1]));
+      a.z       = f2h(__fadd_rn(h2f(a.z), src[2]));
+      a.w       = f2h(__fadd_rn(h2f(a.w), src[3]));
+      reinterpret_cast<ushort4*>(acc)[s] = a;
+      rev[s]                             = f2h(__fmul_rn(h2f(rev[s]), om));
+    }
+  c.nStored++;
+}
+
+template <int S>
+__device__ __forceinline__ void ropSamples(const FragCtx& c, size_t pix, uint32_t mask, const Color4& src)
+{
+  if(isZero(src))
+    return;  // identity blend: encode(decode(v)) == v for every 8-bit v
+  uint32_t* px = c.p.color + pix * S;
+#pragma unroll
+  for(int s = 0; s < S; s++)
+    if(mask & (1u << s))
+      px[s] = ropPremult(c.t, px[s], src);
+}
+
+// one colour-pass invocation + its ROP write
+template <int PASS, int S>
+__device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz)
+{
+  const FrameParams& p   = c.p;
+  const size_t       pix = (size_t)yl * p.W + x;
+  const size_t       ai  = ((size_t)sampleID * p.localH + yl) * p.W + x;
+  if(PASS == PASS_LOOP_DEPTH)
+  {
+    fragLoopDepth(c, pix, sampleID, z);
+    return;
+  }
+  c.nFrag++;
+  Color4 out = zeroColor();
+  switch(PASS)
+  {
+    case PASS_SIMPLE: out = fragSimple(c, pix, ai, sampleID, mask, rgba, z); break;
+    case PASS_LINKEDLIST: out = fragLinkedList(c, ai, mask, rgba, z); break;
+    case PASS_LOOP_COLOR: out = fragLoopColor(c, pix, sampleID, rgba, z); break;
+    case PASS_LOOP64: out = fragLoop64(c, pix, sampleID, rgba, z); break;
+    case PASS_SPINLOCK: out = fragLock<true>(c, pix, ai, sampleID, mask, rgba, z); break;
+    case PASS_INTERLOCK: out = fragLock<false>(c, pix, ai, sampleID, mask, rgba, z); break;
+    case PASS_WEIGHTED: fragWeighted<S>(c, pix, mask, rgba, viewz); return;
+  }
+  ropSamples<S>(c, pix, mask, out);
+}
+
+}  // namespace oit

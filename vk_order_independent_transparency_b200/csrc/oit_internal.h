@@ -81,7 +81,7 @@ struct FrameParams
   uint16_t*            wacc;
   uint16_t*            wrev;
   uint32_t*            fin;
-  const float*         tables;  // [0,256): sRGB8 -> linear, [256,512): encode thresholds
+  const float*         tables;  // [0,256): sRGB8 -> linear, [256,512): encode thresholds, [512,768): v/255
   unsigned long long*  stats;
   // geometry
   const float*    verts;
