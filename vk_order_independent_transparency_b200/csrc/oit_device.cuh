@@ -33,10 +33,12 @@ __device__ __forceinline__ uint32_t enc8(const SrgbTables& t, float c)
   const float cc = fminf(fmaxf(c, 0.f), 1.f);
   const float s  = cc < 0.0031308f ? 12.92f * cc : 1.055f * __powf(cc, 0.41666666f) - 0.055f;
   int         k  = min(max(__float2int_rn(s * 255.0f), 0), 255);
-  while(k > 0 && c < t.thr[k])
-    k--;
-  while(k < 255 && c >= t.thr[k + 1])
-    k++;
+  // the guess is within one code of the exact answer (the intrinsics' error is ~1e-6 of a code step); one branch-free
+  // correction against the two neighbouring thresholds makes it exact.  thr[256] reads the first entry of a255 (= 0),
+  // masked out by k < 255.
+  const float lo = t.thr[k], hi = t.thr[k + 1];
+  k += (k < 255 && c >= hi) ? 1 : 0;
+  k -= (c < lo) ? 1 : 0;
   return (uint32_t)k;
 }
 __device__ __forceinline__ uint32_t unorm8(float a) { return __float2uint_rn(__fmul_rn(clamp01(a), 255.0f)); }

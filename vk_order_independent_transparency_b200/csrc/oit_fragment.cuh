@@ -58,10 +58,22 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
   const float* a0 = p.verts + (size_t)s.vidx[0] * 10;
   const float* a1 = p.verts + (size_t)s.vidx[1] * 10;
   const float* a2 = p.verts + (size_t)s.vidx[2] * 10;
-  float        v[7];
+  // normal (3 floats at byte 12) + colour (4 floats at byte 24) of each vertex: one 32-bit and three 64-bit loads
+  float v0[7], v1[7], v2[7];
+  auto  fetch = [](const float* a, float* o) {
+    o[0]            = __ldg(a + 3);
+    const float2 n  = __ldg(reinterpret_cast<const float2*>(a + 4));
+    const float2 c0 = __ldg(reinterpret_cast<const float2*>(a + 6));
+    const float2 c1 = __ldg(reinterpret_cast<const float2*>(a + 8));
+    o[1] = n.x; o[2] = n.y; o[3] = c0.x; o[4] = c0.y; o[5] = c1.x; o[6] = c1.y;
+  };
+  fetch(a0, v0);
+  fetch(a1, v1);
+  fetch(a2, v2);
+  float v[7];
 #pragma unroll
   for(int k = 0; k < 7; k++)
-    v[k] = __fmul_rn(__fmaf_rn(q2, __ldg(a2 + 3 + k), __fmaf_rn(q1, __ldg(a1 + 3 + k), __fmul_rn(q0, __ldg(a0 + 3 + k)))), rden);
+    v[k] = __fmul_rn(__fmaf_rn(q2, v2[k], __fmaf_rn(q1, v1[k], __fmul_rn(q0, v0[k]))), rden);
   if(NEED_VIEWZ)
     viewz = __fmul_rn(__fmaf_rn(q2, p.tv[s.vidx[2]].viewz, __fmaf_rn(q1, p.tv[s.vidx[1]].viewz, __fmul_rn(q0, p.tv[s.vidx[0]].viewz))), rden);
   const float LX = -0.40824829046386301637f, LY = 0.81649658092772603273f, LZ = 0.40824829046386301637f;
@@ -90,12 +102,12 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
 // buffers); pix = yl * W + x; ai = aux index of (sampleID, pixel).
 
 // K2 oitSimple.frag.glsl:50-91
-__device__ __forceinline__ Color4 fragSimple(FragCtx& c, size_t pix, size_t ai, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z)
+// `old` = imageAtomicAdd(imgAux, coord, 1u), issued by preInvoke() before the shading so that its latency overlaps
+__device__ __forceinline__ Color4 fragSimple(FragCtx& c, size_t pix, uint32_t old, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z)
 {
   const FrameParams& p        = c.p;
   const size_t       viewSize = (size_t)p.W * p.localH;
   const size_t       listPos  = viewSize * p.L * sampleID + pix;
-  const uint32_t     old      = atomicAdd(&p.aux[ai], 1u);
   if(old < (uint32_t)p.L)
   {
     const uint32_t packed = packColor(c.t, rgba);
@@ -114,18 +126,22 @@ __device__ __forceinline__ Color4 fragSimple(FragCtx& c, size_t pix, size_t ai, 
   return zeroColor();
 }
 
-// K4 oitLinkedList.frag.glsl:51-85 -- the single-address counter is bumped once per converged warp group
-__device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t mask, const Color4& rgba, float z)
+// the linked-list allocator (oitLinkedList.frag.glsl:55): the single-address counter is bumped once per converged
+// warp group (warp-aggregated atomicAdd); called before the shading so that the L2 round trip overlaps with it
+__device__ __forceinline__ uint32_t allocLinkedListNode(const FrameParams& p)
+{
+  cg::coalesced_group g    = cg::coalesced_threads();
+  uint32_t            base = 0;
+  if(g.thread_rank() == 0)
+    base = atomicAdd(p.counter, g.size());
+  return g.shfl(base, 0) + g.thread_rank() + 1u;
+}
+
+// K4 oitLinkedList.frag.glsl:51-85.  The head exchange runs with the pixel exclusively owned (tile-ordered arbitration),
+// so imageAtomicExchange is a plain load + store that stays in this SM's L1.
+__device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t newOffset, uint32_t mask, const Color4& rgba, float z)
 {
   const FrameParams& p = c.p;
-  uint32_t           newOffset;
-  {
-    cg::coalesced_group g = cg::coalesced_threads();
-    uint32_t            base = 0;
-    if(g.thread_rank() == 0)
-      base = atomicAdd(p.counter, g.size());
-    newOffset = g.shfl(base, 0) + g.thread_rank() + 1u;
-  }
   if(newOffset >= p.capacity)
   {
     if(p.tailBlend)
@@ -135,7 +151,8 @@ __device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t
     }
     return zeroColor();
   }
-  const uint32_t oldOffset = atomicExch(&p.aux[ai], newOffset);
+  const uint32_t oldOffset = p.aux[ai];
+  p.aux[ai]                = newOffset;
   reinterpret_cast<uint4*>(p.abuf)[newOffset] =
       make_uint4(packColor(c.t, rgba), __float_as_uint(z), p.coverage ? mask : 0u, oldOffset);
   c.nStored++;
@@ -382,9 +399,22 @@ __device__ __forceinline__ void ropSamples(const FragCtx& c, size_t pix, uint32_
       px[s] = ropPremult(c.t, px[s], src);
 }
 
+// the part of an invocation that does not depend on the shaded colour: issued first so that its memory latency is
+// hidden behind the interpolation + shading arithmetic
+template <int PASS>
+__device__ __forceinline__ uint32_t preInvoke(const FrameParams& p, int x, int yl, uint32_t sampleID)
+{
+  if(PASS == PASS_LINKEDLIST)
+    return allocLinkedListNode(p);
+  if(PASS == PASS_SIMPLE)
+    return atomicAdd(&p.aux[((size_t)sampleID * p.localH + yl) * p.W + x], 1u);
+  return 0u;
+}
+
 // one colour-pass invocation + its ROP write
 template <int PASS, int S>
-__device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz)
+__device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz,
+                                       uint32_t token)
 {
   const FrameParams& p   = c.p;
   const size_t       pix = (size_t)yl * p.W + x;
@@ -398,8 +428,8 @@ __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampl
   Color4 out = zeroColor();
   switch(PASS)
   {
-    case PASS_SIMPLE: out = fragSimple(c, pix, ai, sampleID, mask, rgba, z); break;
-    case PASS_LINKEDLIST: out = fragLinkedList(c, ai, mask, rgba, z); break;
+    case PASS_SIMPLE: out = fragSimple(c, pix, token, sampleID, mask, rgba, z); break;
+    case PASS_LINKEDLIST: out = fragLinkedList(c, ai, token, mask, rgba, z); break;
     case PASS_LOOP_COLOR: out = fragLoopColor(c, pix, sampleID, rgba, z); break;
     case PASS_LOOP64: out = fragLoop64(c, pix, sampleID, rgba, z); break;
     case PASS_SPINLOCK: out = fragLock<true>(c, pix, ai, sampleID, mask, rgba, z); break;

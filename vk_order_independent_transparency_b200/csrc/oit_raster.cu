@@ -338,18 +338,20 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
                 {
                   const int    px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
                   const Bary   b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
-                  float        vz = 0.f;
-                  const Color4 rgba = shadeAt<false>(p, s, b, vz);
-                  invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz);
+                  float          vz    = 0.f;
+                  const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
+                  const Color4   rgba  = shadeAt<false>(p, s, b, vz);
+                  invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token);
                 }
             }
             else
             {
               // one invocation per pixel, varyings and gl_FragCoord.z at the pixel centre
               const Bary   bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
-              float        vz = 0.f;
-              const Color4 rgba = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
-              invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz);
+              float          vz    = 0.f;
+              const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
+              const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
+              invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token);
             }
           }
         } while(__syncthreads_or(pending));
