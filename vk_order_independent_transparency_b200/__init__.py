@@ -75,10 +75,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("OIT_B200_LIB", LIB_PATH)  # developer override: alternative builds of the same library
+    if not os.path.exists(path):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(make -C vk_order_independent_transparency_b200/csrc). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp = C.c_void_p
     L.oit_abi_version.restype = C.c_int
     L.oit_default_config.argtypes = [C.POINTER(OitConfig)]

@@ -13,7 +13,10 @@ constexpr int TILE_W      = 16;
 constexpr int TILE_H      = 16;
 constexpr int TILE_PIX    = TILE_W * TILE_H;
 constexpr int TILE_SHIFT  = 4;
-constexpr int RASTER_THREADS = 256;  // = triangles staged per chunk
+#ifndef OIT_RASTER_THREADS
+#define OIT_RASTER_THREADS 256
+#endif
+constexpr int RASTER_THREADS = OIT_RASTER_THREADS;  // = triangles staged per chunk
 constexpr int SUBPIXEL_BITS  = 8;    // fixed-point snapping (NVIDIA and lavapipe use 8)
 constexpr float GUARD_BAND_PX = 2097152.0f;  // |x|,|y| < 2^21 px so every edge delta fits in 31 bits
 

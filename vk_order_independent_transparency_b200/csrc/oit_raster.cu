@@ -6,24 +6,39 @@
 //   ROP blending in primitive order                                              main.cpp:540-592
 //
 // Execution model: one CTA per 16x16 screen tile.  The CTA walks the tile's triangle list (primitive order) in
-// chunks of 256 triangles:
-//   stage   thread t sets up triangle t of the chunk (edge deltas, depth plane, bounding box clipped to the tile) in
-//           shared memory; a CTA scan of the box areas gives every (triangle, pixel) candidate a dense item index.
-//   phase 1 (coverage) each thread tests ITEMS_PER_THREAD consecutive items against the S sample positions (int32 edge
-//           functions for triangles up to 64 px, int64 otherwise; top-left rule; early per-sample depth test) and the
-//           covered ones are compacted IN ITEM ORDER into a shared-memory fragment queue (CTA scan, no atomics).
-//   phase 2 (shade + insert) the queue is consumed 256 dense fragments at a time.  Two fragments of the same pixel in
-//           one round are serialised in queue order through a per-pixel owner word (shared-memory atomicMin), so every
-//           pixel sees its fragments in PRIMITIVE ORDER -- what the hardware ROP guarantees for the tail blend and what
-//           the ordered interlock asks for -- and the technique's A-buffer protocol runs with the pixel exclusively owned.
+// chunks of RASTER_THREADS triangles:
+//   stage    thread t sets up triangle t of the chunk (edge deltas, depth plane, bounding box clipped to the tile) in
+//            shared memory; a CTA scan of the (padded) box areas gives every (triangle, pixel) candidate an item index.
+//   coverage each thread tests ITEMS_PER_THREAD consecutive items of ONE triangle against the S sample positions (int32
+//            edge functions for triangles up to 64 px, int64 otherwise; top-left rule; early per-sample depth test).
+//   tickets  every covered fragment sets bit `thread` in a per-pixel bit set in shared memory; after one barrier its
+//            ticket = popcount of the lower bits = the number of EARLIER fragments of the same pixel in this batch
+//            (item order == thread order == primitive order).  Fragments are bucketed by ticket into layers.
+//   shade    layer 0, then layer 1, ... are processed with one barrier between layers.  A layer holds at most one
+//            fragment per pixel, so inside a layer all lanes run dense and unsynchronised with the pixel exclusively
+//            owned, and across layers every pixel sees its fragments in PRIMITIVE ORDER -- what the hardware ROP
+//            guarantees for the tail blend and what the ordered interlock asks for.
 // A tile is owned by one CTA for the whole pass, so its A-buffer slice, aux words and colour samples stay in one SM's
 // L1 and in L2.
 #include "oit_fragment.cuh"
 
 namespace oit {
 
-constexpr int ITEMS_PER_THREAD = 4;
+#ifndef OIT_ITEMS_PER_THREAD
+#define OIT_ITEMS_PER_THREAD 4
+#endif
+#ifndef OIT_SMEM_CARVEOUT
+#define OIT_SMEM_CARVEOUT -1
+#endif
+#ifndef OIT_USE_DP2A
+#define OIT_USE_DP2A 1
+#endif
+#ifndef OIT_TICKET_MATCH
+#define OIT_TICKET_MATCH 1
+#endif
+constexpr int ITEMS_PER_THREAD = OIT_ITEMS_PER_THREAD;
 constexpr int BATCH_ITEMS      = RASTER_THREADS * ITEMS_PER_THREAD;
+constexpr int MASK_WORDS       = RASTER_THREADS / 32;
 
 template <int S>
 struct SamplePattern;
@@ -52,6 +67,14 @@ struct SamplePattern<8>
   }
 };
 
+// c + lo16(a) * byte0(b) + hi16(a) * byte1(b), a signed halves, b unsigned bytes (SASS IDP.2A.LO.S16.U8)
+__device__ __forceinline__ int dp2aS16U8(int a, uint32_t b, int c)
+{
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // unbiased edge function q (from vertex q+1 to vertex q+2) at a point given in 1/256 px, as a float.
 // SMALL triangles (extent <= 64 px) fit int32; the conversion to float rounds identically either way.
 __device__ __forceinline__ float edgeFloat(const TriSlot& s, int q, int px, int py, bool small)
@@ -72,22 +95,31 @@ __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int g
   uint32_t   mask = 0;
   if(small)
   {
-    int e[3], dxs[3], dys[3];
+    // |dx|, |dy| <= 2^14 fit a signed 16-bit half and the sample offsets an unsigned byte, so one IDP.2A per edge and
+    // sample evaluates e + dx * sy - dy * sx
+    int e[3], pk[3];
 #pragma unroll
     for(int q = 0; q < 3; q++)
     {
       const int a = (q + 1) % 3, b = (q + 2) % 3;
-      dxs[q]      = s.x[b] - s.x[a];
-      dys[q]      = s.y[b] - s.y[a];
-      e[q]        = dxs[q] * (oy - s.y[a]) - dys[q] * (ox - s.x[a]) - (int)((s.box >> (16 + q)) & 1u);
+      const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
+      pk[q]       = (int)(((uint32_t)dx & 0xFFFFu) | ((uint32_t)(-dy) << 16));
+      e[q]        = dx * (oy - s.y[a]) - dy * (ox - s.x[a]) - (int)((s.box >> (16 + q)) & 1u);
     }
 #pragma unroll
     for(int sI = 0; sI < S; sI++)
     {
+#if OIT_USE_DP2A
+      const uint32_t sp = (uint32_t)SamplePattern<S>::y(sI) | ((uint32_t)SamplePattern<S>::x(sI) << 8);
+      const int      e0 = dp2aS16U8(pk[0], sp, e[0]);
+      const int      e1 = dp2aS16U8(pk[1], sp, e[1]);
+      const int      e2 = dp2aS16U8(pk[2], sp, e[2]);
+#else
       const int sx = SamplePattern<S>::x(sI), sy = SamplePattern<S>::y(sI);
-      const int e0 = e[0] + dxs[0] * sy - dys[0] * sx;
-      const int e1 = e[1] + dxs[1] * sy - dys[1] * sx;
-      const int e2 = e[2] + dxs[2] * sy - dys[2] * sx;
+      const int e0 = e[0] + (short)(pk[0] & 0xFFFF) * sy + (pk[0] >> 16) * sx;
+      const int e1 = e[1] + (short)(pk[1] & 0xFFFF) * sy + (pk[1] >> 16) * sx;
+      const int e2 = e[2] + (short)(pk[2] & 0xFFFF) * sy + (pk[2] >> 16) * sx;
+#endif
       if((e0 | e1 | e2) >= 0)
         mask |= 1u << sI;
     }
@@ -133,17 +165,82 @@ __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int g
   return mask;
 }
 
+// one fragment record (slot | lx << 8 | ly << 12 | mask << 16) with its pixel exclusively owned
+template <int PASS, int S, bool SSHADE>
+__device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, uint32_t rec, int tileX0, int tileY0, int yLocal0)
+{
+  const FrameParams& p     = ctx.p;
+  const bool         small = (s.box >> 20) & 1u;
+  const int          lx = (rec >> 8) & 15, ly = (rec >> 12) & 15;
+  const uint32_t     mask = rec >> 16;
+  const int          gx = tileX0 + lx, yl = yLocal0 + ly;
+  const int          ox = gx << 8, oy = (tileY0 + ly) << 8;
+  if(PASS == PASS_OPAQUE)
+  {
+    // opaque.frag.glsl:30-34, BlendMode::NONE with depth write (main.cpp:541-546); shaded at the pixel centre
+    float        vz;
+    const Bary   bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
+    Color4       g  = shadeAt<false>(p, s, bc, vz);
+    g.a             = 1.0f;
+    const uint32_t enc = encodeDst(ctx.t, g);
+    const size_t   pix = (size_t)yl * p.W + gx;
+    bool           wrote = false;
+#pragma unroll
+    for(int sI = 0; sI < S; sI++)
+      if(mask & (1u << sI))
+      {
+        const int   px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
+        const Bary  b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
+        const float zs = depthAt(s, b);
+        // the mask was computed before this pixel's earlier fragments of the same batch ran: test again
+        if(zs < p.depth[pix * S + sI])
+        {
+          p.depth[pix * S + sI] = zs;
+          p.color[pix * S + sI] = enc;
+          wrote                 = true;
+        }
+      }
+    ctx.nOpaque += wrote ? 1u : 0u;
+  }
+  else if(SSHADE && PASS != PASS_WEIGHTED)
+  {
+    // sample shading: every covered sample is its own invocation at the sample position
+#pragma unroll 1
+    for(int sI = 0; sI < S; sI++)
+      if(mask & (1u << sI))
+      {
+        const int      px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
+        const Bary     b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
+        float          vz    = 0.f;
+        const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
+        const Color4   rgba  = shadeAt<false>(p, s, b, vz);
+        invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token);
+      }
+  }
+  else
+  {
+    // one invocation per pixel, varyings and gl_FragCoord.z at the pixel centre
+    const Bary     bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
+    float          vz    = 0.f;
+    const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
+    const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
+    invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token);
+  }
+}
+
 template <int PASS, int S, bool SSHADE>
 __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
 {
   __shared__ SrgbTables tabs;
   __shared__ TriSlot    slots[RASTER_THREADS];
   __shared__ uint32_t   itemStart[RASTER_THREADS + 1];
-  __shared__ uint32_t   queue[BATCH_ITEMS];
-  __shared__ uint32_t   owner[2][TILE_PIX];
+  __shared__ uint32_t   sorted[BATCH_ITEMS];                // fragment records bucketed by layer
+  __shared__ uint32_t   pixMask[TILE_PIX][MASK_WORDS];      // per pixel: which threads hold a fragment of it
+  __shared__ uint32_t   layerCount[2][RASTER_THREADS];      // double buffered across batches
+  __shared__ uint32_t   numLayers[2];
   __shared__ uint32_t   scanSm[33];
 
-  const int      tid  = threadIdx.x;
+  const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const uint32_t listBegin = p.tileStart[tile], listEnd = p.tileStart[tile + 1];
   if(listBegin == listEnd)
@@ -154,8 +251,12 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
   const int yLocal0 = rl * TILE_H;                      // the same row inside this band's buffers
 
   loadTables(tabs, p.tables);
-  owner[0][tid] = 0xFFFFFFFFu;
-  owner[1][tid] = 0xFFFFFFFFu;
+  for(int i = tid; i < TILE_PIX * MASK_WORDS; i += RASTER_THREADS)
+    (&pixMask[0][0])[i] = 0u;
+  layerCount[0][tid] = 0u;
+  layerCount[1][tid] = 0u;
+  if(tid < 2)
+    numLayers[tid] = 0u;
   FragCtx  ctx{p, tabs, 0, 0, 0, 0};
   uint32_t parity = 0;
   const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16), hi = 256 - lo;
@@ -212,7 +313,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
       if(px0 <= px1 && py0 <= py1)
       {
         const int bw = px1 - px0 + 1, bh = py1 - py0 + 1;
-        nItems       = bw * bh;
+        // padded to a multiple of ITEMS_PER_THREAD so that the items of one thread always belong to one triangle
+        nItems = (uint32_t)(bw * bh + ITEMS_PER_THREAD - 1) & ~(uint32_t)(ITEMS_PER_THREAD - 1);
         s.box  = (uint32_t)(px0 - tileX0) | ((uint32_t)(py0 - tileY0) << 4) | ((uint32_t)(bw - 1) << 8) | ((uint32_t)(bh - 1) << 12)
                 | (biasBits << 16) | ((zSafe ? 1u : 0u) << 19) | ((small ? 1u : 0u) << 20);
         s.rcpW = (65535u + bw) / bw;
@@ -230,10 +332,16 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
 
     for(uint32_t k0 = 0; k0 < total; k0 += BATCH_ITEMS)
     {
-      // ---- phase 1: coverage of ITEMS_PER_THREAD consecutive items, ordered compaction ---------------------------
-      uint32_t recs[ITEMS_PER_THREAD];
-      uint32_t nCov  = 0;
-      uint32_t k     = k0 + tid * ITEMS_PER_THREAD;
+      uint32_t* lcount = layerCount[parity & 1u];
+      uint32_t* lnext  = layerCount[(parity & 1u) ^ 1u];
+      uint32_t& nlay   = numLayers[parity & 1u];
+
+      // ---- coverage: ITEMS_PER_THREAD consecutive items of one triangle ---------------------------------------------
+      uint32_t       recs[ITEMS_PER_THREAD];
+      const uint32_t k = k0 + tid * ITEMS_PER_THREAD;
+#pragma unroll
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+        recs[j] = 0u;
       if(k < total)
       {
         int slot = 0;
@@ -241,121 +349,116 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
         for(int step = RASTER_THREADS / 2; step; step >>= 1)
           if(itemStart[slot + step] <= k)
             slot += step;
+        const TriSlot& s      = slots[slot];
+        const uint32_t bw     = ((s.box >> 8) & 15u) + 1u, bh = ((s.box >> 12) & 15u) + 1u;
+        const uint32_t local0 = k - itemStart[slot];
 #pragma unroll
-        for(int j = 0; j < ITEMS_PER_THREAD; j++, k++)
+        for(int j = 0; j < ITEMS_PER_THREAD; j++)
         {
-          if(k < total)
+          const uint32_t local = local0 + j;
+          if(local < bw * bh)
           {
-            while(itemStart[slot + 1] <= k)
-              slot++;
-            const TriSlot& s     = slots[slot];
-            const uint32_t local = k - itemStart[slot];
-            const uint32_t row   = (local * s.rcpW) >> 16;
-            const uint32_t bw    = ((s.box >> 8) & 15u) + 1u;
-            const int      lx    = (int)((s.box & 15u) + (local - row * bw));
-            const int      ly    = (int)(((s.box >> 4) & 15u) + row);
-            const float*   dpx   = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
-            const uint32_t mask  = coverageMask<S>(s, tileX0 + lx, tileY0 + ly, dpx);
-            recs[j]              = (uint32_t)slot | ((uint32_t)lx << 8) | ((uint32_t)ly << 12) | (mask << 16);
-            nCov += mask ? 1u : 0u;
+            const uint32_t row  = (local * s.rcpW) >> 16;
+            const int      lx   = (int)((s.box & 15u) + (local - row * bw));
+            const int      ly   = (int)(((s.box >> 4) & 15u) + row);
+            const float*   dpx  = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
+            const uint32_t mask = coverageMask<S>(s, tileX0 + lx, tileY0 + ly, dpx);
+            if(mask)
+            {
+              recs[j] = (uint32_t)slot | ((uint32_t)lx << 8) | ((uint32_t)ly << 12) | (mask << 16);
+              atomicOr(&pixMask[ly * TILE_W + lx][warp], 1u << lane);
+            }
           }
-          else
-            recs[j] = 0u;
         }
-      }
-      else
-      {
-#pragma unroll
-        for(int j = 0; j < ITEMS_PER_THREAD; j++)
-          recs[j] = 0u;
-      }
-      uint32_t nq;
-      {
-        uint32_t pos = blockExclusiveScan(nCov, scanSm, nq);
-#pragma unroll
-        for(int j = 0; j < ITEMS_PER_THREAD; j++)
-          if(recs[j] >> 16)
-            queue[pos++] = recs[j];
       }
       __syncthreads();
 
-      // ---- phase 2: dense fragments, primitive-ordered per pixel ---------------------------------------------------
-      for(uint32_t q0 = 0; q0 < nq; q0 += RASTER_THREADS)
-      {
-        const uint32_t q       = q0 + tid;
-        bool           pending = q < nq;
-        const uint32_t rec     = pending ? queue[q] : 0u;
-        const int      lx = (rec >> 8) & 15, ly = (rec >> 12) & 15, pl = ly * TILE_W + lx;
-        const uint32_t mask = rec >> 16;
-        do
-        {
-          uint32_t* own = owner[parity & 1u];
-          parity++;
-          if(pending)
-            atomicMin(&own[pl], (uint32_t)tid);
-          __syncthreads();
-          if(pending && own[pl] == (uint32_t)tid)
-          {
-            own[pl] = 0xFFFFFFFFu;
-            pending = false;
-            const TriSlot& s     = slots[rec & 255u];
-            const bool     small = (s.box >> 20) & 1u;
-            const int      gx = tileX0 + lx, yl = yLocal0 + ly;
-            const int      ox = gx << 8, oy = (tileY0 + ly) << 8;
-            if(PASS == PASS_OPAQUE)
-            {
-              // opaque.frag.glsl:30-34, BlendMode::NONE with depth write (main.cpp:541-546); shaded at the pixel centre
-              float        vz;
-              const Bary   bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
-              Color4       g  = shadeAt<false>(p, s, bc, vz);
-              g.a             = 1.0f;
-              const uint32_t enc = encodeDst(tabs, g);
-              const size_t   pix = (size_t)yl * p.W + gx;
-              bool           wrote = false;
+      // ---- tickets: earlier fragments of the same pixel; position inside the layer -----------------------------------
+      uint32_t tick[ITEMS_PER_THREAD], pos[ITEMS_PER_THREAD];
+      uint32_t maxTicket = 0;
 #pragma unroll
-              for(int sI = 0; sI < S; sI++)
-                if(mask & (1u << sI))
-                {
-                  const int   px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
-                  const Bary  b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
-                  const float zs = depthAt(s, b);
-                  // the mask was computed before this pixel's earlier fragments of the same batch ran: test again
-                  if(zs < p.depth[pix * S + sI])
-                  {
-                    p.depth[pix * S + sI] = zs;
-                    p.color[pix * S + sI] = enc;
-                    wrote                 = true;
-                  }
-                }
-              ctx.nOpaque += wrote ? 1u : 0u;
-            }
-            else if(SSHADE && PASS != PASS_WEIGHTED)
-            {
-              // sample shading: every covered sample is its own invocation at the sample position
-#pragma unroll 1
-              for(int sI = 0; sI < S; sI++)
-                if(mask & (1u << sI))
-                {
-                  const int    px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
-                  const Bary   b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
-                  float          vz    = 0.f;
-                  const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
-                  const Color4   rgba  = shadeAt<false>(p, s, b, vz);
-                  invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token);
-                }
-            }
-            else
-            {
-              // one invocation per pixel, varyings and gl_FragCoord.z at the pixel centre
-              const Bary   bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
-              float          vz    = 0.f;
-              const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
-              const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
-              invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token);
-            }
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+      {
+        uint32_t t = 0xFFFFFFFFu;
+        if(recs[j])
+        {
+          const uint32_t* m = pixMask[((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)];
+          t                 = __popc(m[warp] & ((1u << lane) - 1u));
+          for(int w = 0; w < warp; w++)
+            t += __popc(m[w]);
+          maxTicket = max(maxTicket, t + 1u);
+        }
+        tick[j] = t;
+        // claim a slot in the layer's bucket: warp-aggregated for the common tickets 0..2, per thread beyond
+        uint32_t myPos = 0;
+#if OIT_TICKET_MATCH
+        {
+          const uint32_t peers  = __match_any_sync(0xffffffffu, t);
+          const int      leader = __ffs(peers) - 1;
+          uint32_t       first  = 0;
+          if(lane == leader && t != 0xFFFFFFFFu)
+            first = atomicAdd(&lcount[t], __popc(peers));
+          myPos = __shfl_sync(0xffffffffu, first, leader) + __popc(peers & ((1u << lane) - 1u));
+        }
+#else
+#pragma unroll
+        for(uint32_t tv = 0; tv < 3; tv++)
+        {
+          const uint32_t votes = __ballot_sync(0xffffffffu, t == tv);
+          if(votes)
+          {
+            const int leader = __ffs(votes) - 1;
+            uint32_t  first  = 0;
+            if(lane == leader)
+              first = atomicAdd(&lcount[tv], __popc(votes));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if(t == tv)
+              myPos = first + __popc(votes & ((1u << lane) - 1u));
           }
-        } while(__syncthreads_or(pending));
+        }
+        if(t != 0xFFFFFFFFu && t >= 3u)
+          myPos = atomicAdd(&lcount[t], 1u);
+#endif
+        pos[j] = myPos;
       }
+      maxTicket = __reduce_max_sync(0xffffffffu, maxTicket);
+      if(lane == 0 && maxTicket)
+        atomicMax(&nlay, maxTicket);
+      __syncthreads();
+
+      // ---- bucket the records by layer; reset the bit sets and the other batch's counters ----------------------------
+      const uint32_t c0 = lcount[0], c1 = lcount[1], c2 = lcount[2];
+#pragma unroll
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+        if(recs[j])
+        {
+          const uint32_t t = tick[j];
+          uint32_t       b = (t > 0u ? c0 : 0u) + (t > 1u ? c1 : 0u) + (t > 2u ? c2 : 0u);
+          for(uint32_t l = 3; l < t; l++)
+            b += lcount[l];
+          sorted[b + pos[j]] = recs[j];
+          pixMask[((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)][warp] = 0u;
+        }
+      lnext[tid] = 0u;
+      if(tid == 0)
+        numLayers[(parity & 1u) ^ 1u] = 0u;
+      __syncthreads();
+
+      // ---- shade + insert, layer by layer (<= 1 fragment per pixel inside a layer) --------------------------------------
+      const uint32_t nl    = nlay;
+      uint32_t       start = 0;
+      for(uint32_t l = 0; l < nl; l++)
+      {
+        const uint32_t cnt = lcount[l];
+        for(uint32_t i = start + tid; i < start + cnt; i += RASTER_THREADS)
+        {
+          const uint32_t rec = sorted[i];
+          processFragment<PASS, S, SSHADE>(ctx, slots[rec & 255u], rec, tileX0, tileY0, yLocal0);
+        }
+        start += cnt;
+        __syncthreads();
+      }
+      parity++;
     }
     __syncthreads();
   }
@@ -375,26 +478,39 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
 }
 
 // ---- dispatch ----------------------------------------------------------------------------------------------------------
+template <int PASS, int S, bool SSHADE>
+static void launchKernel(const FrameParams& p, unsigned grid, cudaStream_t s)
+{
+  // eight 128-thread CTAs (eight tiles) per SM need ~160 KB of shared memory: ask for a large carveout once
+  static bool configured = false;
+  if(!configured && OIT_SMEM_CARVEOUT >= 0)
+  {
+    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
+    configured = true;
+  }
+  k_raster<PASS, S, SSHADE><<<grid, RASTER_THREADS, 0, s>>>(p);
+}
+
 template <int PASS>
 static void launchPass(const FrameParams& p, cudaStream_t s)
 {
   const unsigned grid = (unsigned)(p.tilesX * p.tileRowsLocal);
   const bool     ss   = p.sampleShading != 0;
   if(p.msaa == 1)
-    k_raster<PASS, 1, false><<<grid, RASTER_THREADS, 0, s>>>(p);
+    launchKernel<PASS, 1, false>(p, grid, s);
   else if(p.msaa == 4)
   {
     if(ss)
-      k_raster<PASS, 4, true><<<grid, RASTER_THREADS, 0, s>>>(p);
+      launchKernel<PASS, 4, true>(p, grid, s);
     else
-      k_raster<PASS, 4, false><<<grid, RASTER_THREADS, 0, s>>>(p);
+      launchKernel<PASS, 4, false>(p, grid, s);
   }
   else
   {
     if(ss)
-      k_raster<PASS, 8, true><<<grid, RASTER_THREADS, 0, s>>>(p);
+      launchKernel<PASS, 8, true>(p, grid, s);
     else
-      k_raster<PASS, 8, false><<<grid, RASTER_THREADS, 0, s>>>(p);
+      launchKernel<PASS, 8, false>(p, grid, s);
   }
 }
 
