@@ -18,7 +18,7 @@ def run_case(alg, aa, tail, W, H, numObjects, subdiv, pct, layers, N, verbose=Fa
                    percentTransparent=pct, oitLayers=layers, linkedListAllocatedPerElement=N)
     verts, idx, ipo = oit.generate_scene(st)
     ubo = oit.default_camera(W, H)
-    s = oit.Sample(st, W, H)
+    s = oit.Sample(st, W, H, keepIntermediates=True)
     s.setScene(verts, idx, ipo)
     t0 = time.time()
     s.onRender(ubo)

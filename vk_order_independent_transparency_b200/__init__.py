@@ -193,11 +193,15 @@ class Sample:
     `onRender(ubo)` is the whole frame; the `clearTransparent*` / `drawTransparent*` methods keep the reference's names and
     split so that tests read like the reference's frame recorder."""
 
-    def __init__(self, state, width, height, device=0, bandCount=1, bandIndex=0, stripRows=32):
+    def __init__(self, state, width, height, device=0, bandCount=1, bandIndex=0, stripRows=32, keepIntermediates=False):
+        """keepIntermediates: onRender keeps m_colorImage (the per-sample colour target) in device memory so that it can
+        be downloaded; by default the frame is fused (colour pass + composite + resolve per tile) and only the A-buffer,
+        the aux images and the resolved frame exist afterwards.  The stage-by-stage calls always keep it."""
         self.L = load_library()
         self.state = state
         self.width, self.height = width, height
         self.cfg = state.to_config(width, height, device, bandCount, bandIndex, stripRows)
+        self.cfg.reserved[0] = 1 if keepIntermediates else 0
         h = C.c_void_p()
         r = self.L.oit_create(C.byref(self.cfg), C.byref(h))
         if r != 0:

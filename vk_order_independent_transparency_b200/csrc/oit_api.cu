@@ -2,6 +2,7 @@
 // (oitRender.cpp:28-154) expressed as kernel launches on one CUDA stream.  See include/oit_b200.h for the contract.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -79,6 +80,17 @@ struct OitCtx
   // binning (0 = transparent draw, 1 = opaque draw)
   BinBuffers bins[2]{};
   uint32_t   pairTotal[2]{};
+  uint32_t   drawTris[2]{};
+  // per-frame UBO in device memory + its pinned staging copy; the captured frame graph
+  DevBuf          uboDev;
+  DeviceUbo*      hostUbo    = nullptr;
+  cudaGraph_t     graph      = nullptr;
+  cudaGraphExec_t graphExec  = nullptr;
+  bool            graphValid = false;
+  bool            useGraph   = true;
+  bool            capturing  = false;  // a frame is being issued without host synchronisation
+  bool            fuseFrame  = false;  // oit_render: colour pass + composite + resolve in one kernel
+  uint64_t        graphLaunches = 0;
   int        sortedBuf[2]{};
   uint32_t*  hostScalar = nullptr;  // pinned
   OitStats   lastStats{};
@@ -133,6 +145,7 @@ void freeBins(BinBuffers& b)
   cudaFree(b.pairVal[0]);
   cudaFree(b.pairVal[1]);
   cudaFree(b.tileStart);
+  cudaFree(b.pairInfo);
   cudaFree(b.scratch);
   b = BinBuffers{};
 }
@@ -152,7 +165,10 @@ int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
     CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
   }
   CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 2 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 2 * sizeof(uint32_t)));
   CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
+  c->graphValid = false;  // the captured frame refers to the old buffers
   return OIT_OK;
 }
 
@@ -168,7 +184,14 @@ void splitObjects(const OitCtx* c, uint32_t& numTransparent, uint32_t& numOpaque
 
 void record(OitCtx* c, int id)
 {
-  cudaEventRecord(c->ev[id], c->stream);
+  // inside a stream capture the stage events become EXTERNAL event-record nodes, so that they are re-recorded by every
+  // replay of the frame graph and cudaEventElapsedTime keeps working on them
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &st);
+  if(st == cudaStreamCaptureStatusActive)
+    cudaEventRecordWithFlags(c->ev[id], c->stream, cudaEventRecordExternal);
+  else
+    cudaEventRecord(c->ev[id], c->stream);
   c->evRecorded[id] = true;
 }
 
@@ -190,40 +213,42 @@ DevBuf* bufferOf(OitCtx* c, OitBuffer which)
   return nullptr;
 }
 
-// bins one draw range; synchronises the stream once to learn the pair count
+// bins one draw range, asynchronously: the pair count stays on the device (BinBuffers::pairInfo)
 int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullBack)
 {
-  BinBuffers&    b        = c->bins[which];
+  BinBuffers&    b         = c->bins[which];
   const uint32_t triPerObj = c->idxPerObj / 3;
   const uint32_t firstTri = firstObj * triPerObj, triCount = numObj * triPerObj;
-  c->pairTotal[which]     = 0;
+  c->drawTris[which]      = triCount;
   if(triCount == 0)
     return OIT_OK;
-  c->launches += launchBinCount(c->fp, b, firstTri, triCount, cullBack, c->stream);
-  CUDA_TRY(c, cudaMemcpyAsync(c->hostScalar, b.counts + triCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  const uint32_t total = *c->hostScalar;
-  if(total > b.pairCapacity)
+  c->launches += launchBin(c->fp, b, firstTri, triCount, cullBack, &c->sortedBuf[which], c->stream);
+  return OIT_OK;
+}
+
+// after a frame: did a pair buffer overflow?  If so grow it (the frame has to be rendered again).
+int growBinsIfNeeded(OitCtx* c, bool* grown)
+{
+  *grown = false;
+  unsigned long long overflow = 0;
+  CUDA_TRY(c, cudaMemcpy(&overflow, (unsigned long long*)c->stats.p + STAT_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost));
+  for(int which = 0; which < 2; which++)
   {
-    // grow: keep the scanned counts (they are the emit offsets)
-    const size_t newCap = (size_t)total + total / 4 + 1024;
-    for(int i = 0; i < 2; i++)
+    BinBuffers& b = c->bins[which];
+    if(!b.pairInfo || c->drawTris[which] == 0)
+      continue;
+    uint32_t info[2] = {0, 0};
+    CUDA_TRY(c, cudaMemcpy(info, b.pairInfo, sizeof(info), cudaMemcpyDeviceToHost));
+    c->pairTotal[which] = info[1];
+    if(overflow && info[1] > b.pairCapacity)
     {
-      cudaFree(b.pairKey[i]);
-      cudaFree(b.pairVal[i]);
-      b.pairKey[i] = b.pairVal[i] = nullptr;
-      CUDA_TRY(c, cudaMalloc(&b.pairKey[i], newCap * sizeof(uint32_t)));
-      CUDA_TRY(c, cudaMalloc(&b.pairVal[i], newCap * sizeof(uint32_t)));
+      const size_t tris = b.triCapacity;
+      const int    r    = allocBins(c, b, tris, (size_t)info[1] + info[1] / 4 + 1024);
+      if(r != OIT_OK)
+        return r;
+      *grown = true;
     }
-    cudaFree(b.scratch);
-    b.scratch      = nullptr;
-    b.pairCapacity = newCap;
-    b.scratchWords = binScratchWords(triCount, newCap, 0);
-    CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
   }
-  c->launches += launchBinEmitSort(c->fp, b, firstTri, triCount, cullBack, total, &c->sortedBuf[which], c->stream);
-  c->pairTotal[which] = total;
-  CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
 }
 
@@ -364,6 +389,9 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   for(int i = 0; i < NUM_EVENTS; i++)
     CREATE_CUDA(cudaEventCreate(&c->ev[i]));
   CREATE_CUDA(cudaMallocHost(&c->hostScalar, 64));
+  CREATE_CUDA(cudaMallocHost(&c->hostUbo, sizeof(DeviceUbo)));
+  memset(c->hostUbo, 0, sizeof(DeviceUbo));
+  c->useGraph = getenv("OIT_B200_NO_GRAPH") == nullptr;
 
   // tile / band geometry
   FrameParams& fp    = c->fp;
@@ -375,6 +403,12 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   fp.L               = (int)cfg->oitLayers;
   fp.tailBlend       = cfg->tailBlend ? 1 : 0;
   fp.layers          = c->sampleShading ? c->msaa : 1;
+  fp.algorithm       = (int)cfg->algorithm;
+  fp.supersample     = c->supersample;
+  fp.fused           = 0;
+  // oit_render fuses composite + resolve into the colour-pass kernel (tile colour in shared memory) unless the caller
+  // asked to keep the intermediate m_colorImage (reserved[0] bit 0) or OIT_LAYERS exceeds the fused kernel's arrays
+  c->fuseFrame = (cfg->reserved[0] & 1u) == 0 && cfg->oitLayers <= 8 && getenv("OIT_B200_NO_FUSE") == nullptr;
   fp.tilesX          = (fp.W + TILE_W - 1) / TILE_W;
   fp.tileRowsGlobal  = (fp.H + TILE_H - 1) / TILE_H;
   fp.stripTileRows   = (int)(stripRows * c->supersample) / TILE_H;
@@ -459,8 +493,8 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   fp.fin     = (uint32_t*)c->fin.p;
   fp.tables  = (const float*)c->tables.p;
   fp.stats   = (unsigned long long*)c->stats.p;
-  fp.alphaMin   = 0.2f;
-  fp.alphaWidth = 0.3f;
+  CREATE_TRY(devAlloc(c, c->uboDev, sizeof(DeviceUbo)));
+  fp.ubo = (const DeviceUbo*)c->uboDev.p;
   *out          = c;
   return OIT_OK;
 #undef CREATE_TRY
@@ -489,6 +523,13 @@ int oit_destroy(OitCtx* c)
       cudaEventDestroy(c->ev[i]);
   if(c->hostScalar)
     cudaFreeHost(c->hostScalar);
+  if(c->hostUbo)
+    cudaFreeHost(c->hostUbo);
+  if(c->graphExec)
+    cudaGraphExecDestroy(c->graphExec);
+  if(c->graph)
+    cudaGraphDestroy(c->graph);
+  devFree(c->uboDev);
   if(c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -522,9 +563,10 @@ int oit_get_dims(const OitCtx* c, uint32_t* bufW, uint32_t* bufH, uint32_t* msaa
 
 static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t indicesPerObject)
 {
-  c->nVerts    = nVerts;
-  c->nIndices  = nIndices;
-  c->idxPerObj = indicesPerObject;
+  c->nVerts     = nVerts;
+  c->nIndices   = nIndices;
+  c->idxPerObj  = indicesPerObject;
+  c->graphValid = false;
   int r        = devAlloc(c, c->tv, (size_t)nVerts * sizeof(TVert));
   if(r != OIT_OK)
     return r;
@@ -554,13 +596,15 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
   c->sceneOwned = true;
   if(c->verts.bytes != (size_t)nVerts * 40)
   {
-    int r = devAlloc(c, c->verts, (size_t)nVerts * 40);
+    c->graphValid = false;
+    int r         = devAlloc(c, c->verts, (size_t)nVerts * 40);
     if(r != OIT_OK)
       return r;
   }
   if(c->indices.bytes != (size_t)nIndices * 4)
   {
-    int r = devAlloc(c, c->indices, (size_t)nIndices * 4);
+    c->graphValid = false;
+    int r         = devAlloc(c, c->indices, (size_t)nIndices * 4);
     if(r != OIT_OK)
       return r;
   }
@@ -605,10 +649,14 @@ int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
   c->ubo.viewport[2] = (int32_t)(c->bufW * c->bufH);
   c->ubo.linkedListAllocatedPerElement =
       c->cfg.algorithm == OIT_LINKEDLIST ? c->fp.capacity : c->cfg.oitLayers * (uint32_t)c->fp.layers;
-  memcpy(c->fp.projView, ubo->projViewMatrix, sizeof(float) * 16);
-  memcpy(c->fp.view, ubo->viewMatrix, sizeof(float) * 16);
-  c->fp.alphaMin   = ubo->alphaMin;
-  c->fp.alphaWidth = ubo->alphaWidth;
+  // the previous frame may still be reading the staging copy
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(c->hostUbo->projView, ubo->projViewMatrix, sizeof(float) * 16);
+  memcpy(c->hostUbo->view, ubo->viewMatrix, sizeof(float) * 16);
+  c->hostUbo->alphaMin   = ubo->alphaMin;
+  c->hostUbo->alphaWidth = ubo->alphaWidth;
+  CUDA_TRY(c, cudaMemcpyAsync(c->uboDev.p, c->hostUbo, sizeof(DeviceUbo), cudaMemcpyHostToDevice, c->stream));
   c->haveUbo       = true;
   return OIT_OK;
 }
@@ -638,6 +686,24 @@ int oit_begin_frame(OitCtx* c)
     return r;
   if((r = binDraw(c, 1, nt, no, true)) != OIT_OK)
     return r;
+  if(!c->capturing)
+  {
+    // stage-by-stage use: make sure the pair buffers were large enough before anything consumes the bins
+    // (oit_render does this check once per frame instead, after the whole asynchronous frame)
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    bool grown = false;
+    if((r = growBinsIfNeeded(c, &grown)) != OIT_OK)
+      return r;
+    if(grown)
+    {
+      CUDA_TRY(c, cudaMemsetAsync(c->stats.p, 0, c->stats.bytes, c->stream));
+      c->launches += launchTransformVertices(c->fp, c->stream);
+      if((r = binDraw(c, 0, 0, nt, false)) != OIT_OK)
+        return r;
+      if((r = binDraw(c, 1, nt, no, true)) != OIT_OK)
+        return r;
+    }
+  }
   record(c, EV_GEOM);
   // clearTransparent* + colour/depth clear
   c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream);
@@ -651,7 +717,7 @@ int oit_draw_opaque(OitCtx* c)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  if(c->pairTotal[1] > 0 && c->fp.depth)
+  if(c->drawTris[1] > 0 && c->fp.depth)
   {
     useBins(c, 1);
     c->launches += launchRaster(c->fp, PASS_OPAQUE, c->stream);
@@ -666,7 +732,7 @@ int oit_draw_transparent(OitCtx* c)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  if(c->pairTotal[0] > 0)
+  if(c->drawTris[0] > 0)
   {
     useBins(c, 0);
     switch(c->cfg.algorithm)
@@ -693,7 +759,8 @@ int oit_composite(OitCtx* c)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  c->launches += launchComposite(c->fp, (int)c->cfg.algorithm, c->stream);
+  if(!c->fp.fused)
+    c->launches += launchComposite(c->fp, (int)c->cfg.algorithm, c->stream);
   record(c, EV_COMPOSITE);
   CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
@@ -704,7 +771,8 @@ int oit_resolve(OitCtx* c)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  c->launches += launchResolve(c->fp, c->supersample, (int)c->cfg.width, (int)c->localOutH, c->stream);
+  if(!c->fp.fused)
+    c->launches += launchResolve(c->fp, c->supersample, (int)c->cfg.width, (int)c->localOutH, c->stream);
   record(c, EV_RESOLVE);
   CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
@@ -719,11 +787,10 @@ int oit_synchronize(OitCtx* c)
   return OIT_OK;
 }
 
-int oit_render(OitCtx* c, const OitSceneData* ubo)
+// every stage of one frame, asynchronously on the context's stream
+static int issueFrame(OitCtx* c)
 {
   int r;
-  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
-    return r;
   if((r = oit_begin_frame(c)) != OIT_OK)
     return r;
   if((r = oit_draw_opaque(c)) != OIT_OK)
@@ -732,9 +799,81 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     return r;
   if((r = oit_composite(c)) != OIT_OK)
     return r;
-  if((r = oit_resolve(c)) != OIT_OK)
+  return oit_resolve(c);
+}
+
+int oit_render(OitCtx* c, const OitSceneData* ubo)
+{
+  int r;
+  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
     return r;
-  return oit_synchronize(c);
+  if(!c->verts.p || !c->indices.p)
+    return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
+  for(int attempt = 0; attempt < 4; attempt++)
+  {
+    if((r = ensureSceneBins(c)) != OIT_OK)
+      return r;
+    c->capturing = true;  // the frame is issued without host synchronisation; overflow is checked once at the end
+    {
+      // the fused kernel is the transparent colour pass: without transparent triangles the staged kernels resolve the frame
+      uint32_t nt = 0, no = 0;
+      splitObjects(c, nt, no);
+      c->fp.fused = (c->fuseFrame && nt > 0) ? 1 : 0;
+    }
+    if(c->useGraph)
+    {
+      // the whole frame (~30 kernels) is captured once and replayed as one graph launch
+      if(!c->graphValid)
+      {
+        if(c->graphExec)
+          cudaGraphExecDestroy(c->graphExec);
+        if(c->graph)
+          cudaGraphDestroy(c->graph);
+        c->graphExec = nullptr;
+        c->graph     = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        if(e == cudaSuccess)
+        {
+          r = issueFrame(c);
+          e = cudaStreamEndCapture(c->stream, &c->graph);
+          if(r == OIT_OK && e == cudaSuccess)
+            e = cudaGraphInstantiate(&c->graphExec, c->graph, 0);
+        }
+        if(r != OIT_OK || e != cudaSuccess)
+        {
+          cudaGetLastError();
+          c->useGraph  = false;  // fall back to plain stream launches
+          c->capturing = false;
+    c->fp.fused  = 0;
+          continue;
+        }
+        c->graphValid    = true;
+        c->graphLaunches = c->launches;
+      }
+      c->launches = c->graphLaunches;
+      cudaError_t e = cudaGraphLaunch(c->graphExec, c->stream);
+      if(e != cudaSuccess)
+      {
+        c->capturing = false;
+    c->fp.fused  = 0;
+        return fail(c, OIT_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+      }
+    }
+    else
+      r = issueFrame(c);
+    c->capturing = false;
+    c->fp.fused  = 0;
+    if(r != OIT_OK)
+      return r;
+    if((r = oit_synchronize(c)) != OIT_OK)
+      return r;
+    bool grown = false;
+    if((r = growBinsIfNeeded(c, &grown)) != OIT_OK)
+      return r;
+    if(!grown)
+      return OIT_OK;
+  }
+  return fail(c, OIT_ERR_OUT_OF_MEMORY, "the (tile, triangle) pair buffers kept overflowing");
 }
 
 int oit_get_stats(OitCtx* c, OitStats* out)
@@ -766,6 +905,7 @@ int oit_get_stats(OitCtx* c, OitStats* out)
     float t = 0.f;
     if(c->evRecorded[a] && c->evRecorded[b] && cudaEventElapsedTime(&t, c->ev[a], c->ev[b]) == cudaSuccess)
       return t;
+    cudaGetLastError();  // do not leave a sticky error behind for the host application
     return 0.f;
   };
   s.msGeometry  = ms(EV_START, EV_GEOM);

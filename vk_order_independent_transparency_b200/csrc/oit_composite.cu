@@ -66,7 +66,8 @@ int launchClears(const FrameParams& p, int algorithm, cudaStream_t s)
       n += fill32(p.wrev, (P * p.msaa + 1) / 2, 0x3C003C00u, s);  // R16F 1.0
       break;
   }
-  n += fill32(p.color, P * p.msaa, p.clearColor, s);
+  if(!(p.fused && p.depth == nullptr))  // the fused frame kernel keeps the colour tile in shared memory
+    n += fill32(p.color, P * p.msaa, p.clearColor, s);
   if(p.depth)
     n += fill32(p.depth, P * p.msaa, 0x3F800000u, s);
   return n;

@@ -93,7 +93,7 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
   c.r = __fmul_rn(v[3], __fmaf_rn(0.0f, om, warmth));
   c.g = __fmul_rn(v[4], __fmaf_rn(0.25f, om, warmth));
   c.b = __fmul_rn(v[5], __fmaf_rn(0.75f, om, warmth));
-  c.a = clamp01(__fmaf_rn(v[6], p.alphaWidth, p.alphaMin));
+  c.a = clamp01(__fmaf_rn(v[6], p.ubo->alphaWidth, p.ubo->alphaMin));
   return c;
 }
 
@@ -388,11 +388,11 @@ __device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, uint32_t ma
 }
 
 template <int S>
-__device__ __forceinline__ void ropSamples(const FragCtx& c, size_t pix, uint32_t mask, const Color4& src)
+// px: the S colour samples of the pixel -- in m_colorImage, or in the shared-memory tile of the fused frame kernel
+__device__ __forceinline__ void ropSamples(const FragCtx& c, uint32_t* px, uint32_t mask, const Color4& src)
 {
   if(isZero(src))
     return;  // identity blend: encode(decode(v)) == v for every 8-bit v
-  uint32_t* px = c.p.color + pix * S;
 #pragma unroll
   for(int s = 0; s < S; s++)
     if(mask & (1u << s))
@@ -414,7 +414,7 @@ __device__ __forceinline__ uint32_t preInvoke(const FrameParams& p, int x, int y
 // one colour-pass invocation + its ROP write
 template <int PASS, int S>
 __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz,
-                                       uint32_t token)
+                                       uint32_t token, uint32_t* colorPx)
 {
   const FrameParams& p   = c.p;
   const size_t       pix = (size_t)yl * p.W + x;
@@ -436,7 +436,7 @@ __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampl
     case PASS_INTERLOCK: out = fragLock<false>(c, pix, ai, sampleID, mask, rgba, z); break;
     case PASS_WEIGHTED: fragWeighted<S>(c, pix, mask, rgba, viewz); return;
   }
-  ropSamples<S>(c, pix, mask, out);
+  ropSamples<S>(c, colorPx, mask, out);
 }
 
 }  // namespace oit

@@ -3,6 +3,10 @@
 // Replaces: object.vert.glsl:32-38 (K0), the fixed-function viewport transform and primitive assembly
 // (main.cpp:504-532) of the reference.  Output: per (local) screen tile, the list of triangles whose sample
 // bounding box touches it, IN PRIMITIVE ORDER -- the order the ROP and the ordered interlock rely on.
+//
+// Everything here is asynchronous: the number of (tile, triangle) pairs stays on the device (the sort and the range
+// kernels read it from memory, grids are sized for the buffer capacity), so a whole frame can be replayed as one CUDA
+// graph.  If the pair buffer is too small an overflow flag is raised and the host grows it and renders again.
 #include "oit_device.cuh"
 
 namespace oit {
@@ -12,7 +16,9 @@ namespace oit {
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
 {
-  const float hw = 0.5f * (float)p.W, hh = 0.5f * (float)p.H;
+  const float  hw = 0.5f * (float)p.W, hh = 0.5f * (float)p.H;
+  const float* M = p.ubo->projView;
+  const float* V = p.ubo->view;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nVerts; i += gridDim.x * blockDim.x)
   {
     const float* v  = p.verts + (size_t)i * 10;
@@ -20,9 +26,9 @@ __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
     float        clip[4];
 #pragma unroll
     for(int r = 0; r < 4; r++)
-      clip[r] = __fmaf_rn(p.projView[0 + r], px, __fmaf_rn(p.projView[4 + r], py, __fmaf_rn(p.projView[8 + r], pz, p.projView[12 + r])));
+      clip[r] = __fmaf_rn(M[0 + r], px, __fmaf_rn(M[4 + r], py, __fmaf_rn(M[8 + r], pz, M[12 + r])));
     TVert t;
-    t.viewz = __fmaf_rn(p.view[2], px, __fmaf_rn(p.view[6], py, __fmaf_rn(p.view[10], pz, p.view[14])));
+    t.viewz = __fmaf_rn(V[2], px, __fmaf_rn(V[6], py, __fmaf_rn(V[10], pz, V[14])));
     t.x     = INT32_MIN;
     t.y     = 0;
     t.z     = 0.f;
@@ -58,15 +64,16 @@ int launchTransformVertices(const FrameParams& p, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------------------
 struct TileRange
 {
-  int tx0, tx1, ty0, ty1;  // global tile coordinates, inclusive; empty if tx0 > tx1
+  int tx0, tx1, ty0, ty1;  // global tile coordinates, inclusive
 };
 
 // The pixel range that can contain a covered sample: a sample of pixel px lies at px*256 + off, off in [lo, hi].
-__device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri, bool cullBack, TileRange& r)
+__device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri, bool cullBack, TileRange& r, bool& rejected)
 {
   const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
   const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
-  if(a.x == INT32_MIN || b.x == INT32_MIN || c.x == INT32_MIN)
+  rejected         = a.x == INT32_MIN || b.x == INT32_MIN || c.x == INT32_MIN;
+  if(rejected)
     return false;
   const long long area2 = (long long)(b.x - a.x) * (c.y - a.y) - (long long)(c.x - a.x) * (b.y - a.y);
   if(area2 == 0 || (cullBack && area2 > 0))
@@ -88,41 +95,48 @@ __device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri,
 __global__ void __launch_bounds__(256) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
                                                    uint32_t* __restrict__ counts)
 {
-  unsigned long long rejected = 0;
+  unsigned long long nRejected = 0;
   for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
   {
     TileRange r;
     uint32_t  n = 0;
-    if(triTileRange(p, firstTri + t, cullBack != 0, r))
+    bool      rejected;
+    if(triTileRange(p, firstTri + t, cullBack != 0, r, rejected))
     {
       const int nx = r.tx1 - r.tx0 + 1;
       for(int R = r.ty0; R <= r.ty1; R++)
         if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
           n += nx;
     }
-    else
-    {
-      const uint32_t* ix = p.indices + 3 * (size_t)(firstTri + t);
-      if(p.tv[ix[0]].x == INT32_MIN || p.tv[ix[1]].x == INT32_MIN || p.tv[ix[2]].x == INT32_MIN)
-        rejected++;
-    }
+    nRejected += rejected ? 1u : 0u;
     counts[t] = n;
   }
-  if(rejected)
-    atomicAdd(&p.stats[STAT_REJECTED], rejected);
+  if(nRejected)
+    atomicAdd(&p.stats[STAT_REJECTED], nRejected);
 }
 
+// offsets[t] = exclusive prefix of the counts, offsets[triCount] = number of pairs.  Pairs beyond `capacity` are dropped
+// and the overflow flag is raised (the host then grows the buffers and renders the frame again).
 __global__ void __launch_bounds__(256) k_bin_emit(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
                                                   const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ vals)
+                                                  uint32_t* __restrict__ vals, uint32_t capacity, uint32_t* __restrict__ pairInfo)
 {
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const uint32_t total = offsets[triCount];
+    pairInfo[0]          = total > capacity ? 0u : total;  // pairs present (none when the frame has to be redone)
+    pairInfo[1]          = total;                 // pairs wanted
+    if(total > capacity)
+      atomicAdd(&p.stats[STAT_OVERFLOW], 1ull);
+  }
   for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
   {
     const uint32_t o0 = offsets[t], o1 = offsets[t + 1];
-    if(o0 == o1)
+    if(o0 == o1 || o1 > capacity)
       continue;
     TileRange r;
-    triTileRange(p, firstTri + t, cullBack != 0, r);
+    bool      rejected;
+    triTileRange(p, firstTri + t, cullBack != 0, r, rejected);
     uint32_t o = o0;
     for(int R = r.ty0; R <= r.ty1; R++)
       if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
@@ -223,43 +237,51 @@ static int launchScan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scr
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stable LSD radix sort of (key, value) pairs on 8-bit digits
+// stable LSD radix sort of (key, value) pairs on 8-bit digits; the element count is read from device memory
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ROUNDS  = 16;
 constexpr int SORT_TILE    = SORT_THREADS * SORT_ROUNDS;
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, size_t n, int shift,
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nPtr, int shift,
                                                             uint32_t* __restrict__ table, uint32_t nb)
 {
   __shared__ uint32_t hist[256];
-  hist[threadIdx.x] = 0;
+  const size_t        n = *nPtr;
+  hist[threadIdx.x]     = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * SORT_TILE;
-#pragma unroll 4
-  for(int r = 0; r < SORT_ROUNDS; r++)
+  if(base < n)
   {
-    const size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
-    if(i < n)
-      atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+#pragma unroll 4
+    for(int r = 0; r < SORT_ROUNDS; r++)
+    {
+      const size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
+      if(i < n)
+        atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
   }
   __syncthreads();
   table[(size_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn,
-                                                               uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, size_t n,
-                                                               int shift, const uint32_t* __restrict__ table, uint32_t nb)
+                                                               uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut,
+                                                               const uint32_t* __restrict__ nPtr, int shift,
+                                                               const uint32_t* __restrict__ table, uint32_t nb)
 {
   __shared__ uint32_t off[256];
   __shared__ uint32_t cnt[SORT_THREADS / 32][256];
-  const int           lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t        n    = *nPtr;
+  const size_t        base = (size_t)blockIdx.x * SORT_TILE;
+  if(base >= n)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   off[threadIdx.x] = table[(size_t)threadIdx.x * nb + blockIdx.x];
 #pragma unroll
   for(int w = 0; w < SORT_THREADS / 32; w++)
     cnt[w][threadIdx.x] = 0;
   __syncthreads();
-  const size_t base = (size_t)blockIdx.x * SORT_TILE;
   for(int r = 0; r < SORT_ROUNDS; r++)
   {
     const size_t   i      = base + (size_t)r * SORT_THREADS + threadIdx.x;
@@ -297,9 +319,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* _
 }
 
 // tileStart[t] = index of the first pair whose key is >= t; tileStart[numTiles] = n
-__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ keys, uint32_t n, uint32_t numTiles,
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ nPtr, uint32_t numTiles,
                                                      uint32_t* __restrict__ tileStart)
 {
+  const uint32_t n = *nPtr;
+  if(n == 0)
+  {
+    for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= numTiles; t += gridDim.x * blockDim.x)
+      tileStart[t] = 0;
+    return;
+  }
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
   {
     const uint32_t k    = keys[i];
@@ -319,50 +348,44 @@ size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t /*numTiles*/
   return scanBlocks(triCount) + 2 + table + scanBlocks(table) + 2;
 }
 
-int launchBinCount(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, cudaStream_t s)
-{
-  if(triCount == 0)
-  {
-    cudaMemsetAsync(b.counts, 0, sizeof(uint32_t), s);
-    return 0;
-  }
-  const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
-  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts);
-  return 1 + launchScan(b.counts, b.counts, triCount, b.scratch, s);
-}
-
-int launchBinEmitSort(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
-                      uint32_t pairTotal, int* sortedBuf, cudaStream_t s)
+// Bins the triangles [firstTri, firstTri + triCount) of the index buffer.  On return (asynchronously) b.pairInfo[0] holds
+// the number of pairs, b.pairVal[*sortedBuf] the triangle lists and b.tileStart the per-tile ranges.
+int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
+              cudaStream_t s)
 {
   const uint32_t numTiles = (uint32_t)p.tilesX * p.tileRowsLocal;
   int            launches = 0;
   *sortedBuf              = 0;
-  if(pairTotal == 0 || triCount == 0)
+  if(triCount == 0 || numTiles == 0)
   {
     cudaMemsetAsync(b.tileStart, 0, sizeof(uint32_t) * (numTiles + 1), s);
+    cudaMemsetAsync(b.pairInfo, 0, sizeof(uint32_t) * 2, s);
     return 0;
   }
   const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
-  k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairKey[0], b.pairVal[0]);
+  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts);
+  launches += 1 + launchScan(b.counts, b.counts, triCount, b.scratch, s);
+  k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairKey[0], b.pairVal[0],
+                                    (uint32_t)b.pairCapacity, b.pairInfo);
   launches++;
   int bits = 1;
   while((1u << bits) < numTiles)
     bits++;
-  const uint32_t nb        = (uint32_t)((pairTotal + SORT_TILE - 1) / SORT_TILE);
+  const uint32_t nb        = (uint32_t)((b.pairCapacity + SORT_TILE - 1) / SORT_TILE);
   uint32_t*      table     = b.scratch + scanBlocks(triCount) + 2;
   uint32_t*      tableScan = table + (size_t)256 * nb + 1;
   int            cur       = 0;
   for(int shift = 0; shift < bits; shift += 8)
   {
-    k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], pairTotal, shift, table, nb);
+    k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairInfo, shift, table, nb);
     launches += 1 + launchScan(table, table, (size_t)256 * nb, tableScan, s);
-    k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairVal[cur], b.pairKey[cur ^ 1], b.pairVal[cur ^ 1], pairTotal,
-                                               shift, table, nb);
+    k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairVal[cur], b.pairKey[cur ^ 1], b.pairVal[cur ^ 1], b.pairInfo, shift,
+                                               table, nb);
     launches++;
     cur ^= 1;
   }
-  const int rblocks = (int)min((pairTotal + 255u) / 256u, 148u * 16u);
-  k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], pairTotal, numTiles, b.tileStart);
+  const int rblocks = (int)min((uint32_t)((b.pairCapacity + 255u) / 256u), 148u * 8u);
+  k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], b.pairInfo, numTiles, b.tileStart);
   launches++;
   *sortedBuf = cur;
   return launches;

@@ -52,8 +52,16 @@ enum StatSlot
   STAT_TAIL,
   STAT_OPAQUE,
   STAT_REJECTED,
-  STAT_PAIRS,
+  STAT_OVERFLOW,  // the (tile, triangle) pair buffer of a draw was too small: the frame must be rendered again
   NUM_STAT_SLOTS = 8
+};
+
+struct DeviceUbo
+{
+  float projView[16];
+  float view[16];
+  float alphaMin, alphaWidth;
+  float pad[2];
 };
 
 struct FrameParams
@@ -66,13 +74,14 @@ struct FrameParams
   int      tailBlend;
   int      layers;    // A-buffer / aux layers (msaa if sample shading)
   uint32_t clearColor;  // (0.2,0.2,0.2,0.2) linear encoded to BGRA8 sRGB (oitRender.cpp:90)
+  int      algorithm;   // OIT_*
+  int      supersample; // 1 or 2
+  int      fused;       // the colour-pass kernel also composites and resolves its tile (oit_render fast path)
   // tiles
   int tilesX, tileRowsGlobal, tileRowsLocal;
   int stripTileRows, bandCount, bandIndex;
-  // UBO scalars
-  float alphaMin, alphaWidth;
-  float projView[16];
-  float view[16];
+  // the per-frame part of shaderio::SceneData, in device memory so that a captured frame graph can be replayed
+  const DeviceUbo* ubo;
   // buffers (device)
   uint32_t*            abuf;
   uint32_t*            aux;
@@ -116,15 +125,14 @@ struct BinBuffers
   uint32_t* pairKey[2];  // [pairCapacity]
   uint32_t* pairVal[2];
   uint32_t* tileStart;   // [numLocalTiles + 1]
+  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics)
   uint32_t* scratch;     // scan / histogram scratch
   size_t    scratchWords;
   size_t    pairCapacity;
   size_t    triCapacity;
 };
-int launchBinCount(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
-                   cudaStream_t s);
-int launchBinEmitSort(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack,
-                      uint32_t pairTotal, int* sortedBuf, cudaStream_t s);
+int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
+              cudaStream_t s);
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
 
 int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);

@@ -21,6 +21,7 @@
 // A tile is owned by one CTA for the whole pass, so its A-buffer slice, aux words and colour samples stay in one SM's
 // L1 and in L2.
 #include "oit_fragment.cuh"
+#include "oit_fused.cuh"
 
 namespace oit {
 
@@ -167,7 +168,8 @@ __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int g
 
 // one fragment record (slot | lx << 8 | ly << 12 | mask << 16) with its pixel exclusively owned
 template <int PASS, int S, bool SSHADE>
-__device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, uint32_t rec, int tileX0, int tileY0, int yLocal0)
+__device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, uint32_t rec, int tileX0, int tileY0, int yLocal0,
+                                                uint32_t* tileColor)
 {
   const FrameParams& p     = ctx.p;
   const bool         small = (s.box >> 20) & 1u;
@@ -175,6 +177,8 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
   const uint32_t     mask = rec >> 16;
   const int          gx = tileX0 + lx, yl = yLocal0 + ly;
   const int          ox = gx << 8, oy = (tileY0 + ly) << 8;
+  // the pixel's colour samples: the shared-memory tile of the fused frame kernel, else m_colorImage
+  uint32_t* colorPx = tileColor ? tileColor + (ly * TILE_W + lx) * S : p.color + ((size_t)yl * p.W + gx) * S;
   if(PASS == PASS_OPAQUE)
   {
     // opaque.frag.glsl:30-34, BlendMode::NONE with depth write (main.cpp:541-546); shaded at the pixel centre
@@ -214,7 +218,7 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
         float          vz    = 0.f;
         const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
         const Color4   rgba  = shadeAt<false>(p, s, b, vz);
-        invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token);
+        invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token, colorPx);
       }
   }
   else
@@ -224,35 +228,64 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
     float          vz    = 0.f;
     const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
     const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
-    invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token);
+    invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token, colorPx);
   }
 }
 
 template <int PASS, int S, bool SSHADE>
 __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
 {
+  // the per-chunk structures (triangle slots, bucketed fragment records, per-pixel thread bit sets) are dead once the
+  // tile's list has been walked: the fused composite reuses their shared memory for its per-pixel fragment arrays
+  constexpr size_t SLOT_BYTES = sizeof(TriSlot) * RASTER_THREADS, SORTED_BYTES = sizeof(uint32_t) * BATCH_ITEMS,
+                   MASK_BYTES = sizeof(uint32_t) * TILE_PIX * MASK_WORDS;
+  constexpr size_t SCRATCH_BYTES = SLOT_BYTES + SORTED_BYTES + MASK_BYTES > sizeof(FusedArrays) ? SLOT_BYTES + SORTED_BYTES + MASK_BYTES : sizeof(FusedArrays);
+  __shared__ __align__(16) unsigned char scratch[SCRATCH_BYTES];
   __shared__ SrgbTables tabs;
-  __shared__ TriSlot    slots[RASTER_THREADS];
   __shared__ uint32_t   itemStart[RASTER_THREADS + 1];
-  __shared__ uint32_t   sorted[BATCH_ITEMS];                // fragment records bucketed by layer
-  __shared__ uint32_t   pixMask[TILE_PIX][MASK_WORDS];      // per pixel: which threads hold a fragment of it
   __shared__ uint32_t   layerCount[2][RASTER_THREADS];      // double buffered across batches
+  __shared__ uint32_t   tileColorSm[TILE_PIX * S];          // colour samples of the tile (fused frame kernel only)
+  TriSlot*  slots   = reinterpret_cast<TriSlot*>(scratch);
+  uint32_t* sorted  = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES);               // fragment records bucketed by layer
+  uint32_t* pixMask = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES + SORTED_BYTES);  // per pixel: which threads hold a fragment
   __shared__ uint32_t   numLayers[2];
   __shared__ uint32_t   scanSm[33];
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const uint32_t listBegin = p.tileStart[tile], listEnd = p.tileStart[tile + 1];
-  if(listBegin == listEnd)
+  const bool     fused = PASS != PASS_OPAQUE && PASS != PASS_LOOP_DEPTH && p.fused != 0;
+  if(listBegin == listEnd && !fused)
     return;
   const int rl = tile / p.tilesX, tx = tile - rl * p.tilesX;
   const int R  = tileRowToGlobal(rl, p.stripTileRows, p.bandCount, p.bandIndex);
   const int tileX0 = tx * TILE_W, tileY0 = R * TILE_H;  // global pixel origin of the tile
   const int yLocal0 = rl * TILE_H;                      // the same row inside this band's buffers
 
+  uint32_t* tileColor = fused ? tileColorSm : nullptr;
+  if(fused)
+  {
+    // the tile's colour samples start as the cleared (or opaque-drawn) m_colorImage content
+    for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
+    {
+      const int pl = i / S, gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
+      uint32_t  v  = p.clearColor;
+      if(p.depth != nullptr && gx < p.W && tileY0 + ly < p.H)
+        v = p.color[((size_t)(yLocal0 + ly) * p.W + gx) * S + (i - pl * S)];
+      tileColorSm[i] = v;
+    }
+    if(listBegin == listEnd)
+    {
+      // nothing transparent touches this tile: resolve what is there
+      loadTables(tabs, p.tables);
+      __syncthreads();
+      fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
+      return;
+    }
+  }
   loadTables(tabs, p.tables);
   for(int i = tid; i < TILE_PIX * MASK_WORDS; i += RASTER_THREADS)
-    (&pixMask[0][0])[i] = 0u;
+    pixMask[i] = 0u;
   layerCount[0][tid] = 0u;
   layerCount[1][tid] = 0u;
   if(tid < 2)
@@ -366,7 +399,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
             if(mask)
             {
               recs[j] = (uint32_t)slot | ((uint32_t)lx << 8) | ((uint32_t)ly << 12) | (mask << 16);
-              atomicOr(&pixMask[ly * TILE_W + lx][warp], 1u << lane);
+              atomicOr(&pixMask[(ly * TILE_W + lx) * MASK_WORDS + warp], 1u << lane);
             }
           }
         }
@@ -382,7 +415,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
         uint32_t t = 0xFFFFFFFFu;
         if(recs[j])
         {
-          const uint32_t* m = pixMask[((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)];
+          const uint32_t* m = pixMask + (((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)) * MASK_WORDS;
           t                 = __popc(m[warp] & ((1u << lane) - 1u));
           for(int w = 0; w < warp; w++)
             t += __popc(m[w]);
@@ -437,7 +470,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
           for(uint32_t l = 3; l < t; l++)
             b += lcount[l];
           sorted[b + pos[j]] = recs[j];
-          pixMask[((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)][warp] = 0u;
+          pixMask[(((recs[j] >> 12) & 15u) * TILE_W + ((recs[j] >> 8) & 15u)) * MASK_WORDS + warp] = 0u;
         }
       lnext[tid] = 0u;
       if(tid == 0)
@@ -453,7 +486,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
         for(uint32_t i = start + tid; i < start + cnt; i += RASTER_THREADS)
         {
           const uint32_t rec = sorted[i];
-          processFragment<PASS, S, SSHADE>(ctx, slots[rec & 255u], rec, tileX0, tileY0, yLocal0);
+          processFragment<PASS, S, SSHADE>(ctx, slots[rec & 255u], rec, tileX0, tileY0, yLocal0, tileColor);
         }
         start += cnt;
         __syncthreads();
@@ -461,6 +494,22 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(const FrameParams p)
       parity++;
     }
     __syncthreads();
+  }
+
+  // ---- fused frame: composite + resolve of the tile while its A-buffer slice is still in L1 / L2 --------------------------
+  if(fused)
+  {
+    FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
+    __threadfence_block();
+    __syncthreads();
+    for(int pl = tid; pl < TILE_PIX; pl += RASTER_THREADS)
+    {
+      const int gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
+      if(gx < p.W && tileY0 + ly < p.H)
+        fusedCompositePixel<S>(p, tabs, A, pl, (size_t)(yLocal0 + ly) * p.W + gx, tileColorSm + pl * S);
+    }
+    __syncthreads();
+    fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
   }
 
   // ---- statistics ----------------------------------------------------------------------------------------------------
