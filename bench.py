@@ -33,6 +33,15 @@ WORKLOADS = {
 TECH_TABLE = [(a, 0) for a in range(7)]  # per-technique table at 3840x2160, no AA, default parameters
 
 
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -52,7 +61,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -249,7 +258,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(verts.nbytes + idx.nbytes + 224), "d2h_bytes_per_step": int(s.localRows * W * 4),
                     "note": "scene (vertices + indices) and UBO uploaded from pinned host memory and the resolved strips read back every step"},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "stage": dom, "alg_bytes_per_launch": int(bytes_stage[dom]),
+                         "traffic": measured_traffic(args.workload) if (world == 1 and dom == "color") else None, "peak_source": peak_src, "stage": dom, "alg_bytes_per_launch": int(bytes_stage[dom]),
                          "frame": {"alg_bytes": int(frame_bytes), "achieved": frame_bytes / (frame_ms * 1e-3) / 1e9,
                                    "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak}},
             "clocks": clocks,
