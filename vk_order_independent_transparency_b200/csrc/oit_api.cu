@@ -90,6 +90,8 @@ struct OitCtx
   bool            useGraph   = true;
   bool            capturing  = false;  // a frame is being issued without host synchronisation
   bool            fuseFrame  = false;  // oit_render: colour pass + composite + resolve in one kernel
+  unsigned long long* hostMirror  = nullptr;  // pinned: statistics + pair counts copied back by the frame itself
+  bool                mirrorValid = false;
   uint64_t        graphLaunches = 0;
   int        sortedBuf[2]{};
   uint32_t*  hostScalar = nullptr;  // pinned
@@ -230,15 +232,23 @@ int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullB
 int growBinsIfNeeded(OitCtx* c, bool* grown)
 {
   *grown = false;
+  // oit_render mirrors the counters into pinned host memory at the end of the (captured) frame: no extra round trips
+  const bool         mirrored = c->mirrorValid;
   unsigned long long overflow = 0;
-  CUDA_TRY(c, cudaMemcpy(&overflow, (unsigned long long*)c->stats.p + STAT_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost));
+  if(mirrored)
+    overflow = c->hostMirror[STAT_OVERFLOW];
+  else
+    CUDA_TRY(c, cudaMemcpy(&overflow, (unsigned long long*)c->stats.p + STAT_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost));
   for(int which = 0; which < 2; which++)
   {
     BinBuffers& b = c->bins[which];
     if(!b.pairInfo || c->drawTris[which] == 0)
       continue;
     uint32_t info[2] = {0, 0};
-    CUDA_TRY(c, cudaMemcpy(info, b.pairInfo, sizeof(info), cudaMemcpyDeviceToHost));
+    if(mirrored)
+      memcpy(info, c->hostMirror + NUM_STAT_SLOTS + which, sizeof(info));
+    else
+      CUDA_TRY(c, cudaMemcpy(info, b.pairInfo, sizeof(info), cudaMemcpyDeviceToHost));
     c->pairTotal[which] = info[1];
     if(overflow && info[1] > b.pairCapacity)
     {
@@ -390,6 +400,8 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
     CREATE_CUDA(cudaEventCreate(&c->ev[i]));
   CREATE_CUDA(cudaMallocHost(&c->hostScalar, 64));
   CREATE_CUDA(cudaMallocHost(&c->hostUbo, sizeof(DeviceUbo)));
+  CREATE_CUDA(cudaMallocHost(&c->hostMirror, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long)));
+  memset(c->hostMirror, 0, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long));
   memset(c->hostUbo, 0, sizeof(DeviceUbo));
   c->useGraph = getenv("OIT_B200_NO_GRAPH") == nullptr;
 
@@ -525,6 +537,8 @@ int oit_destroy(OitCtx* c)
     cudaFreeHost(c->hostScalar);
   if(c->hostUbo)
     cudaFreeHost(c->hostUbo);
+  if(c->hostMirror)
+    cudaFreeHost(c->hostMirror);
   if(c->graphExec)
     cudaGraphExecDestroy(c->graphExec);
   if(c->graph)
@@ -799,7 +813,15 @@ static int issueFrame(OitCtx* c)
     return r;
   if((r = oit_composite(c)) != OIT_OK)
     return r;
-  return oit_resolve(c);
+  if((r = oit_resolve(c)) != OIT_OK)
+    return r;
+  // mirror the statistics and the pair counts into pinned host memory as the last nodes of the frame
+  CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror, c->stats.p, NUM_STAT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  for(int which = 0; which < 2; which++)
+    if(c->bins[which].pairInfo && c->drawTris[which] > 0)
+      CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror + NUM_STAT_SLOTS + which, c->bins[which].pairInfo, 2 * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, c->stream));
+  return OIT_OK;
 }
 
 int oit_render(OitCtx* c, const OitSceneData* ubo)
@@ -867,8 +889,11 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
       return r;
     if((r = oit_synchronize(c)) != OIT_OK)
       return r;
-    bool grown = false;
-    if((r = growBinsIfNeeded(c, &grown)) != OIT_OK)
+    bool grown     = false;
+    c->mirrorValid = true;
+    r              = growBinsIfNeeded(c, &grown);
+    c->mirrorValid = false;
+    if(r != OIT_OK)
       return r;
     if(!grown)
       return OIT_OK;
