@@ -62,8 +62,11 @@ int launchClears(const FrameParams& p, int algorithm, cudaStream_t s)
         n += fill32(p.spin, auxWords, 0u, s);
       break;
     case OIT_WEIGHTED:
-      n += fill32(p.wacc, P * p.msaa * 2, 0u, s);               // RGBA16F (0,0,0,0)
-      n += fill32(p.wrev, (P * p.msaa + 1) / 2, 0x3C003C00u, s);  // R16F 1.0
+      if(!p.fused)  // the fused frame kernel keeps the WBOIT targets of a tile in shared memory
+      {
+        n += fill32(p.wacc, P * p.msaa * 2, 0u, s);               // RGBA16F (0,0,0,0)
+        n += fill32(p.wrev, (P * p.msaa + 1) / 2, 0x3C003C00u, s);  // R16F 1.0
+      }
       break;
   }
   if(!(p.fused && p.depth == nullptr))  // the fused frame kernel keeps the colour tile in shared memory

@@ -25,6 +25,9 @@ struct FragCtx
   const FrameParams& p;
   const SrgbTables&  t;
   uint32_t           nFrag, nStored, nTail, nOpaque;
+  // WBOIT targets of the tile in shared memory (fused frame kernel) or nullptr = the global RGBA16F / R16F images
+  uint2*    wAccTile;
+  uint16_t* wRevTile;
 };
 
 __device__ __forceinline__ uint32_t ldcg32(const uint32_t* a) { return __ldcg(a); }
@@ -354,7 +357,7 @@ __device__ __forceinline__ Color4 fragLock(FragCtx& c, size_t pix, size_t ai, ui
 
 // K15 oitWeighted.frag.glsl:53-79 + BlendMode::WEIGHTED_COLOR into RGBA16F / R16F (main.cpp:559-575)
 template <int S>
-__device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, uint32_t mask, const Color4& rgba, float viewz)
+__device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, int pl, uint32_t mask, const Color4& rgba, float viewz)
 {
   const FrameParams& p   = c.p;
   const Color4       col = premultiply(rgba);
@@ -370,19 +373,21 @@ __device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, uint32_t ma
   const float weight = __fmul_rn(aw, distWeight);
   const float om     = __fsub_rn(1.0f, col.a);
   const float src[4] = {__fmul_rn(col.r, weight), __fmul_rn(col.g, weight), __fmul_rn(col.b, weight), __fmul_rn(col.a, weight)};
-  uint16_t*   acc    = p.wacc + pix * S * 4;
-  uint16_t*   rev    = p.wrev + pix * S;
+  // the pixel's S accumulator / revealage samples: shared-memory tile (fused frame) or the global images
+  uint2*    acc = c.wAccTile ? c.wAccTile + pl * S : reinterpret_cast<uint2*>(p.wacc) + pix * S;
+  uint16_t* rev = c.wRevTile ? c.wRevTile + pl * S : p.wrev + pix * S;
 #pragma unroll
   for(int s = 0; s < S; s++)
     if(mask & (1u << s))
     {
-      ushort4 a = reinterpret_cast<ushort4*>(acc)[s];
-      a.x       = f2h(__fadd_rn(h2f(a.x), src[0]));
-      a.y       = f2h(__fadd_rn(h2f(a.y), src[1]));
-      a.z       = f2h(__fadd_rn(h2f(a.z), src[2]));
-      a.w       = f2h(__fadd_rn(h2f(a.w), src[3]));
-      reinterpret_cast<ushort4*>(acc)[s] = a;
-      rev[s]                             = f2h(__fmul_rn(h2f(rev[s]), om));
+      // ROP add on RGBA16F: fp16 -> fp32, add, round to nearest even back to fp16, two channels per conversion
+      const uint2   a  = acc[s];
+      const float2  rg = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+      const float2  ba = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+      const __half2 nrg = __floats2half2_rn(__fadd_rn(rg.x, src[0]), __fadd_rn(rg.y, src[1]));
+      const __half2 nba = __floats2half2_rn(__fadd_rn(ba.x, src[2]), __fadd_rn(ba.y, src[3]));
+      acc[s]            = make_uint2(*reinterpret_cast<const uint32_t*>(&nrg), *reinterpret_cast<const uint32_t*>(&nba));
+      rev[s]            = f2h(__fmul_rn(h2f(rev[s]), om));
     }
   c.nStored++;
 }
@@ -414,7 +419,7 @@ __device__ __forceinline__ uint32_t preInvoke(const FrameParams& p, int x, int y
 // one colour-pass invocation + its ROP write
 template <int PASS, int S>
 __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz,
-                                       uint32_t token, uint32_t* colorPx)
+                                       uint32_t token, uint32_t* colorPx, int pl)
 {
   const FrameParams& p   = c.p;
   const size_t       pix = (size_t)yl * p.W + x;
@@ -434,7 +439,7 @@ __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampl
     case PASS_LOOP64: out = fragLoop64(c, pix, sampleID, rgba, z); break;
     case PASS_SPINLOCK: out = fragLock<true>(c, pix, ai, sampleID, mask, rgba, z); break;
     case PASS_INTERLOCK: out = fragLock<false>(c, pix, ai, sampleID, mask, rgba, z); break;
-    case PASS_WEIGHTED: fragWeighted<S>(c, pix, mask, rgba, viewz); return;
+    case PASS_WEIGHTED: fragWeighted<S>(c, pix, pl, mask, rgba, viewz); return;
   }
   ropSamples<S>(c, colorPx, mask, out);
 }

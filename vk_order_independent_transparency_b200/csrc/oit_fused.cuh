@@ -192,8 +192,10 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
 }
 
 // composite (+ its ROP onto the shared-memory colour tile) of the tile pixel owned by thread t
+// wAcc / wRev: the pixel's S WBOIT accumulator / revealage samples (shared-memory tile), only used for OIT_WEIGHTED
 template <int S>
-__device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, size_t pix, uint32_t* px)
+__device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, size_t pix, uint32_t* px,
+                                                    const uint2* wAcc = nullptr, const uint16_t* wRev = nullptr)
 {
   if(p.algorithm == OIT_WEIGHTED)
   {
@@ -202,10 +204,12 @@ __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const 
     for(int s = 0; s < S; s++)
     {
       const size_t  idx = pix * S + s;
-      const ushort4 acc = reinterpret_cast<const ushort4*>(p.wacc)[idx];
+      const uint2   raw = wAcc ? wAcc[s] : reinterpret_cast<const uint2*>(p.wacc)[idx];
+      const ushort4 acc = make_ushort4((unsigned short)(raw.x & 0xFFFFu), (unsigned short)(raw.x >> 16), (unsigned short)(raw.y & 0xFFFFu),
+                                       (unsigned short)(raw.y >> 16));
       const float   a3  = h2f(acc.w);
       const float   den = a3 > 1e-5f ? a3 : 1e-5f;
-      const Color4  src{__fdiv_rn(h2f(acc.x), den), __fdiv_rn(h2f(acc.y), den), __fdiv_rn(h2f(acc.z), den), h2f(p.wrev[idx])};
+      const Color4  src{__fdiv_rn(h2f(acc.x), den), __fdiv_rn(h2f(acc.y), den), __fdiv_rn(h2f(acc.z), den), h2f(wRev ? wRev[s] : p.wrev[idx])};
       px[s] = ropWeightedComposite(tb, px[s], src);
     }
     return;

@@ -218,7 +218,7 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
         float          vz    = 0.f;
         const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
         const Color4   rgba  = shadeAt<false>(p, s, b, vz);
-        invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token, colorPx);
+        invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token, colorPx, ly * TILE_W + lx);
       }
   }
   else
@@ -228,7 +228,7 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
     float          vz    = 0.f;
     const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
     const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
-    invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token, colorPx);
+    invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token, colorPx, ly * TILE_W + lx);
   }
 }
 
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   __shared__ SrgbTables tabs;
   __shared__ uint32_t   itemStart[RASTER_THREADS + 1];
   __shared__ uint32_t   layerCount[2][RASTER_THREADS];      // double buffered across batches
-  __shared__ uint32_t   tileColorSm[TILE_PIX * S];          // colour samples of the tile (fused frame kernel only)
+  extern __shared__ __align__(16) unsigned char dynSmem[];  // fused frame kernel only: see rasterDynamicSmem()
   TriSlot*  slots   = reinterpret_cast<TriSlot*>(scratch);
   uint32_t* sorted  = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES);               // fragment records bucketed by layer
   uint32_t* pixMask = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES + SORTED_BYTES);  // per pixel: which threads hold a fragment
@@ -266,9 +266,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   const int tileX0 = tx * TILE_W, tileY0 = R * TILE_H;  // global pixel origin of the tile
   const int yLocal0 = rl * TILE_H;                      // the same row inside this band's buffers
 
-  uint32_t* tileColor = fused ? tileColorSm : nullptr;
-  if(fused)
-  {
+  // dynamic shared memory of the fused frame kernel: the tile's colour samples -- or, for WBOIT, the tile's RGBA16F
+  // accumulator + R16F revealage samples (WBOIT does not touch the colour target until its composite, which then uses
+  // the scratch area for the colour tile)
+  constexpr bool WEIGHTED     = PASS == PASS_WEIGHTED;
+  uint32_t*      tileColorSm  = reinterpret_cast<uint32_t*>(WEIGHTED ? scratch : dynSmem);
+  uint2*         wAccSm       = reinterpret_cast<uint2*>(dynSmem);
+  uint16_t*      wRevSm       = reinterpret_cast<uint16_t*>(dynSmem + sizeof(uint2) * TILE_PIX * S);
+  auto           initColorTile = [&]() {
     // the tile's colour samples start as the cleared (or opaque-drawn) m_colorImage content
     for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
     {
@@ -278,6 +283,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
         v = p.color[((size_t)(yLocal0 + ly) * p.W + gx) * S + (i - pl * S)];
       tileColorSm[i] = v;
     }
+  };
+  uint32_t* tileColor = (fused && !WEIGHTED) ? tileColorSm : nullptr;
+  if(fused)
+  {
+    if(!WEIGHTED || listBegin == listEnd)
+      initColorTile();
     if(listBegin == listEnd)
     {
       // nothing transparent touches this tile: resolve what is there
@@ -286,6 +297,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
       fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
       return;
     }
+    if(WEIGHTED)
+      for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
+      {
+        wAccSm[i] = make_uint2(0u, 0u);  // accum cleared to 0, reveal to 1.0 (oitRender.cpp:394-397)
+        wRevSm[i] = 0x3C00u;
+      }
   }
   loadTables(tabs, p.tables);
   for(int i = tid; i < TILE_PIX * MASK_WORDS; i += RASTER_THREADS)
@@ -294,7 +311,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   layerCount[1][tid] = 0u;
   if(tid < 2)
     numLayers[tid] = 0u;
-  FragCtx  ctx{p, tabs, 0, 0, 0, 0};
+  FragCtx  ctx{p, tabs, 0, 0, 0, 0, (fused && WEIGHTED) ? wAccSm : nullptr, (fused && WEIGHTED) ? wRevSm : nullptr};
   uint32_t parity = 0;
   const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16), hi = 256 - lo;
   __syncthreads();
@@ -506,11 +523,17 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
     FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
     __threadfence_block();
     __syncthreads();
+    if(WEIGHTED)
+    {
+      initColorTile();  // into the scratch area, which the chunk structures no longer need
+      __syncthreads();
+    }
     for(int pl = tid; pl < TILE_PIX; pl += RASTER_THREADS)
     {
       const int gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
       if(gx < p.W && tileY0 + ly < p.H)
-        fusedCompositePixel<S>(p, tabs, A, pl, (size_t)(yLocal0 + ly) * p.W + gx, tileColorSm + pl * S);
+        fusedCompositePixel<S>(p, tabs, A, pl, (size_t)(yLocal0 + ly) * p.W + gx, tileColorSm + pl * S, WEIGHTED ? wAccSm + pl * S : nullptr,
+                               WEIGHTED ? wRevSm + pl * S : nullptr);
     }
     __syncthreads();
     fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
@@ -535,13 +558,18 @@ template <int PASS, int S, bool SSHADE>
 static void launchKernel(const FrameParams& p, unsigned grid, cudaStream_t s)
 {
   // eight 128-thread CTAs (eight tiles) per SM need ~160 KB of shared memory: ask for a large carveout once
-  static bool configured = false;
-  if(!configured && OIT_SMEM_CARVEOUT >= 0)
+  // dynamic shared memory of the fused frame kernel: the colour tile, or the RGBA16F + R16F WBOIT tiles (10 B / sample)
+  constexpr size_t dynBytes = (size_t)TILE_PIX * S * (PASS == PASS_WEIGHTED ? 10 : 4);
+  static bool      configured = false;
+  if(!configured)
   {
-    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
+    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynBytes);
+    if(OIT_SMEM_CARVEOUT >= 0)
+      cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
     configured = true;
   }
-  k_raster<PASS, S, SSHADE><<<grid, RASTER_THREADS, 0, s>>>(p);
+  const bool fused = p.fused && PASS != PASS_OPAQUE && PASS != PASS_LOOP_DEPTH;
+  k_raster<PASS, S, SSHADE><<<grid, RASTER_THREADS, fused ? dynBytes : 0, s>>>(p);
 }
 
 template <int PASS>
