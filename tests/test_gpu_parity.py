@@ -263,6 +263,18 @@ def test_reuse_and_idempotence(oit_mod, oracle_mod):
     s.close()
 
 
+@pytest.mark.parametrize("mode", ["onchip_all", "no_onchip", "no_fuse", "no_graph"])
+@pytest.mark.parametrize("alg,aa,L", [(0, 0, 8), (0, 1, 4), (3, 0, 8), (3, 4, 2), (4, 1, 8), (5, 0, 8), (5, 4, 4), (6, 4, 8), (1, 1, 8)])
+def test_frame_path_variants(oit_mod, oracle_mod, monkeypatch, mode, alg, aa, L):
+    """Every way oit_render can execute a frame gives the oracle's image: k-buffer slice in shared memory for all
+    techniques that support it, in HBM for all, staged (unfused) kernels, and plain stream launches instead of the graph."""
+    monkeypatch.setenv({"onchip_all": "OIT_B200_ONCHIP_ALL", "no_onchip": "OIT_B200_NO_ONCHIP", "no_fuse": "OIT_B200_NO_FUSE",
+                        "no_graph": "OIT_B200_NO_GRAPH"}[mode], "1")
+    s, o = run_pair(oit_mod, oracle_mod, 176, 120, algorithm=alg, aaType=aa, oitLayers=L, numObjects=180, subdiv=7)
+    assert_frames_equal(s, o)
+    s.close()
+
+
 def test_error_paths(oit_mod):
     s = oit_mod.Sample(oit_mod.State(algorithm=1), 64, 64)
     with pytest.raises(oit_mod.OitError) as e:

@@ -841,6 +841,15 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
       uint32_t nt = 0, no = 0;
       splitObjects(c, nt, no);
       c->fp.fused = (c->fuseFrame && nt > 0) ? 1 : 0;
+      // k-buffer techniques without sample shading: the tile's A-buffer slice also stays in shared memory
+      const uint32_t words = onChipWords((int)c->cfg.algorithm, (int)c->cfg.oitLayers, c->coverage ? 1 : 0);
+      // measured on B200 (4K, no AA): pays off for the atomic-heavy Loop64 and Spinlock protocols; Simple / Interlock lose
+      // more from the lower occupancy (3 instead of 5 CTAs per SM) than they gain, unless OIT_B200_ONCHIP_ALL is set
+      const bool worthIt = c->cfg.algorithm == OIT_LOOP64 || c->cfg.algorithm == OIT_SPINLOCK || getenv("OIT_B200_ONCHIP_ALL") != nullptr;
+      c->fp.onChip = (c->fp.fused && !c->sampleShading && words > 0 && words * 4u <= ON_CHIP_MAX_BYTES && worthIt
+                      && getenv("OIT_B200_NO_ONCHIP") == nullptr)
+                         ? 1
+                         : 0;
     }
     if(c->useGraph)
     {
@@ -867,6 +876,7 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
           c->useGraph  = false;  // fall back to plain stream launches
           c->capturing = false;
     c->fp.fused  = 0;
+    c->fp.onChip = 0;
           continue;
         }
         c->graphValid    = true;
@@ -878,6 +888,7 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
       {
         c->capturing = false;
     c->fp.fused  = 0;
+    c->fp.onChip = 0;
         return fail(c, OIT_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
       }
     }
@@ -885,6 +896,7 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
       r = issueFrame(c);
     c->capturing = false;
     c->fp.fused  = 0;
+    c->fp.onChip = 0;
     if(r != OIT_OK)
       return r;
     if((r = oit_synchronize(c)) != OIT_OK)

@@ -41,7 +41,7 @@ int launchClears(const FrameParams& p, int algorithm, cudaStream_t s)
   const size_t P        = (size_t)p.W * p.localH;
   const size_t auxWords = P * p.layers;
   int          n        = 0;
-  switch(algorithm)
+  switch(p.onChip ? -1 : algorithm)  // on chip: the fused frame kernel clears its shared-memory slice itself
   {
     case OIT_SIMPLE: n += fill32(p.aux, auxWords, 0u, s); break;
     case OIT_LINKEDLIST:

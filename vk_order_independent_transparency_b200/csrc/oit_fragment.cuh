@@ -28,10 +28,20 @@ struct FragCtx
   // WBOIT targets of the tile in shared memory (fused frame kernel) or nullptr = the global RGBA16F / R16F images
   uint2*    wAccTile;
   uint16_t* wRevTile;
+  // the A-buffer slice + aux words the fragment programs work on: the global buffers (viewSize = W * localH, pixel index
+  // = yl * W + x), or -- fused frame kernel, k-buffer techniques -- the tile's slice in shared memory (viewSize = 256,
+  // pixel index = position inside the tile), addressed with the reference's own index arithmetic either way
+  uint32_t* abuf;
+  uint32_t* aux;
+  uint32_t* adepth;
+  uint32_t* spin;
+  size_t    viewSize;
+  bool      onChip;
 };
 
-__device__ __forceinline__ uint32_t ldcg32(const uint32_t* a) { return __ldcg(a); }
-__device__ __forceinline__ unsigned long long ldcg64(const unsigned long long* a) { return __ldcg(a); }
+// loads of words that atomics of this kernel modify: L2 (ld.cg) for the global buffers, plain for the shared-memory slice
+__device__ __forceinline__ uint32_t ldcg32(const FragCtx& c, const uint32_t* a) { return c.onChip ? *a : __ldcg(a); }
+__device__ __forceinline__ unsigned long long ldcg64(const FragCtx& c, const unsigned long long* a) { return c.onChip ? *a : __ldcg(a); }
 
 // ---- varyings + shading -------------------------------------------------------------------------------------------
 struct Bary
@@ -109,15 +119,15 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
 __device__ __forceinline__ Color4 fragSimple(FragCtx& c, size_t pix, uint32_t old, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z)
 {
   const FrameParams& p        = c.p;
-  const size_t       viewSize = (size_t)p.W * p.localH;
+  const size_t       viewSize = c.viewSize;
   const size_t       listPos  = viewSize * p.L * sampleID + pix;
   if(old < (uint32_t)p.L)
   {
     const uint32_t packed = packColor(c.t, rgba);
     if(p.coverage)
-      reinterpret_cast<uint4*>(p.abuf)[listPos + (size_t)old * viewSize] = make_uint4(packed, __float_as_uint(z), mask, 0u);
+      reinterpret_cast<uint4*>(c.abuf)[listPos + (size_t)old * viewSize] = make_uint4(packed, __float_as_uint(z), mask, 0u);
     else
-      reinterpret_cast<uint2*>(p.abuf)[listPos + (size_t)old * viewSize] = make_uint2(packed, __float_as_uint(z));
+      reinterpret_cast<uint2*>(c.abuf)[listPos + (size_t)old * viewSize] = make_uint2(packed, __float_as_uint(z));
     c.nStored++;
     return zeroColor();
   }
@@ -154,9 +164,9 @@ __device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t
     }
     return zeroColor();
   }
-  const uint32_t oldOffset = p.aux[ai];
-  p.aux[ai]                = newOffset;
-  reinterpret_cast<uint4*>(p.abuf)[newOffset] =
+  const uint32_t oldOffset = c.aux[ai];
+  c.aux[ai]                = newOffset;
+  reinterpret_cast<uint4*>(c.abuf)[newOffset] =
       make_uint4(packColor(c.t, rgba), __float_as_uint(z), p.coverage ? mask : 0u, oldOffset);
   c.nStored++;
   return zeroColor();
@@ -166,14 +176,14 @@ __device__ __forceinline__ Color4 fragLinkedList(FragCtx& c, size_t ai, uint32_t
 __device__ __forceinline__ void fragLoopDepth(FragCtx& c, size_t pix, uint32_t sampleID, float z)
 {
   const FrameParams& p        = c.p;
-  const size_t       viewSize = (size_t)p.W * p.localH;
-  uint32_t*          list     = p.abuf + viewSize * p.L * 2 * sampleID + pix;
+  const size_t       viewSize = c.viewSize;
+  uint32_t*          list     = c.abuf + viewSize * p.L * 2 * sampleID + pix;
   uint32_t           zcur     = __float_as_uint(z);
   int                i        = 0;
-  uint32_t           pretest  = ldcg32(list + (size_t)(p.L - 1) * viewSize);
+  uint32_t           pretest  = ldcg32(c, list + (size_t)(p.L - 1) * viewSize);
   if(zcur > pretest)
     return;
-  pretest = ldcg32(list + (size_t)(p.L / 2) * viewSize);
+  pretest = ldcg32(c, list + (size_t)(p.L / 2) * viewSize);
   if(zcur > pretest)
     i = p.L / 2;
   for(; i < p.L; i++)
@@ -188,8 +198,8 @@ __device__ __forceinline__ void fragLoopDepth(FragCtx& c, size_t pix, uint32_t s
 __device__ __forceinline__ Color4 fragLoopColor(FragCtx& c, size_t pix, uint32_t sampleID, const Color4& rgba, float z)
 {
   const FrameParams& p        = c.p;
-  const size_t       viewSize = (size_t)p.W * p.localH;
-  uint32_t*          list     = p.abuf + viewSize * p.L * 2 * sampleID + pix;
+  const size_t       viewSize = c.viewSize;
+  uint32_t*          list     = c.abuf + viewSize * p.L * 2 * sampleID + pix;
   const uint32_t     zcur     = __float_as_uint(z);
   if(list[(size_t)(p.L - 1) * viewSize] < zcur)
   {
@@ -219,17 +229,17 @@ __device__ __forceinline__ Color4 fragLoopColor(FragCtx& c, size_t pix, uint32_t
 __device__ __forceinline__ Color4 fragLoop64(FragCtx& c, size_t pix, uint32_t sampleID, const Color4& rgba, float z)
 {
   const FrameParams&  p        = c.p;
-  const size_t        viewSize = (size_t)p.W * p.localH;
-  unsigned long long* list     = reinterpret_cast<unsigned long long*>(p.abuf) + viewSize * p.L * sampleID + pix;
+  const size_t        viewSize = c.viewSize;
+  unsigned long long* list     = reinterpret_cast<unsigned long long*>(c.abuf) + viewSize * p.L * sampleID + pix;
   unsigned long long  zcur     = ((unsigned long long)__float_as_uint(z) << 32) | packColor(c.t, rgba);
   int                 i        = 0;
   bool                canInsert = true;
-  unsigned long long  pretest   = ldcg64(list + (size_t)(p.L - 1) * viewSize);
+  unsigned long long  pretest   = ldcg64(c, list + (size_t)(p.L - 1) * viewSize);
   if(zcur > pretest)
     canInsert = false;
   else
   {
-    pretest = ldcg64(list + (size_t)(p.L / 2) * viewSize);
+    pretest = ldcg64(c, list + (size_t)(p.L / 2) * viewSize);
     if(zcur > pretest)
       i = p.L / 2;
   }
@@ -266,16 +276,16 @@ __device__ __forceinline__ bool lockCriticalSection(FragCtx& c, size_t pix, size
                                                     uint32_t zbits, Color4& color)
 {
   const FrameParams& p        = c.p;
-  const size_t       viewSize = (size_t)p.W * p.localH;
+  const size_t       viewSize = c.viewSize;
   const size_t       listPos  = viewSize * p.L * sampleID + pix;
-  const uint32_t     oldCounter = p.aux[ai];
-  p.aux[ai]                     = oldCounter + 1u;
+  const uint32_t     oldCounter = c.aux[ai];
+  c.aux[ai]                     = oldCounter + 1u;
   if(oldCounter < (uint32_t)p.L)
   {
     if(p.coverage)
-      reinterpret_cast<uint4*>(p.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint4(packed, zbits, mask, 0u);
+      reinterpret_cast<uint4*>(c.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint4(packed, zbits, mask, 0u);
     else
-      reinterpret_cast<uint2*>(p.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint2(packed, zbits);
+      reinterpret_cast<uint2*>(c.abuf)[listPos + (size_t)oldCounter * viewSize] = make_uint2(packed, zbits);
     color = zeroColor();
     return true;
   }
@@ -284,7 +294,7 @@ __device__ __forceinline__ bool lockCriticalSection(FragCtx& c, size_t pix, size
   for(int i = 0; i < p.L; i++)
   {
     const size_t   e         = listPos + (size_t)i * viewSize;
-    const uint32_t testDepth = p.coverage ? p.abuf[e * 4 + 1] : p.abuf[e * 2 + 1];
+    const uint32_t testDepth = p.coverage ? c.abuf[e * 4 + 1] : c.abuf[e * 2 + 1];
     if(testDepth > maxDepth)
     {
       maxDepth = testDepth;
@@ -296,15 +306,15 @@ __device__ __forceinline__ bool lockCriticalSection(FragCtx& c, size_t pix, size
     const size_t e = listPos + (size_t)furthest * viewSize;
     if(p.coverage)
     {
-      color                               = unpackColor(c.t, p.abuf[e * 4]);
-      reinterpret_cast<uint4*>(p.abuf)[e] = make_uint4(packed, zbits, mask, 0u);
+      color                               = unpackColor(c.t, c.abuf[e * 4]);
+      reinterpret_cast<uint4*>(c.abuf)[e] = make_uint4(packed, zbits, mask, 0u);
     }
     else
     {
-      color                               = unpackColor(c.t, p.abuf[e * 2]);
-      reinterpret_cast<uint2*>(p.abuf)[e] = make_uint2(packed, zbits);
+      color                               = unpackColor(c.t, c.abuf[e * 2]);
+      reinterpret_cast<uint2*>(c.abuf)[e] = make_uint2(packed, zbits);
     }
-    p.adepth[ai] = maxDepth;
+    c.adepth[ai] = maxDepth;
     return true;
   }
   return false;
@@ -322,18 +332,18 @@ __device__ __forceinline__ Color4 fragLock(FragCtx& c, size_t pix, size_t ai, ui
   bool               stored = false;
   if(SPIN)
   {
-    const uint32_t oldDepth = ldcg32(&p.adepth[ai]);  // racy-but-conservative early-out outside the lock (:67-68)
+    const uint32_t oldDepth = ldcg32(c, &c.adepth[ai]);  // racy-but-conservative early-out outside the lock (:67-68)
     if(zbits <= oldDepth)
     {
       bool done = mask == 0;
       while(!done)
       {
-        const uint32_t old = atomicExch(&p.spin[ai], 1u);
+        const uint32_t old = atomicExch(&c.spin[ai], 1u);
         if(old == 0u)
         {
           stored = lockCriticalSection(c, pix, ai, sampleID, mask, packed, zbits, color);
           __threadfence();
-          atomicExch(&p.spin[ai], 0u);
+          atomicExch(&c.spin[ai], 0u);
           done = true;
         }
       }
@@ -342,7 +352,7 @@ __device__ __forceinline__ Color4 fragLock(FragCtx& c, size_t pix, size_t ai, ui
   else
   {
     // beginInvocationInterlock .. endInvocationInterlock: the arbitration loop of the caller IS the ordered interlock
-    if(zbits <= p.adepth[ai])
+    if(zbits <= c.adepth[ai])
       stored = lockCriticalSection(c, pix, ai, sampleID, mask, packed, zbits, color);
   }
   if(stored)
@@ -407,12 +417,12 @@ __device__ __forceinline__ void ropSamples(const FragCtx& c, uint32_t* px, uint3
 // the part of an invocation that does not depend on the shaded colour: issued first so that its memory latency is
 // hidden behind the interpolation + shading arithmetic
 template <int PASS>
-__device__ __forceinline__ uint32_t preInvoke(const FrameParams& p, int x, int yl, uint32_t sampleID)
+__device__ __forceinline__ uint32_t preInvoke(const FragCtx& c, size_t pixA, uint32_t sampleID)
 {
   if(PASS == PASS_LINKEDLIST)
-    return allocLinkedListNode(p);
+    return allocLinkedListNode(c.p);
   if(PASS == PASS_SIMPLE)
-    return atomicAdd(&p.aux[((size_t)sampleID * p.localH + yl) * p.W + x], 1u);
+    return atomicAdd(&c.aux[(size_t)sampleID * c.viewSize + pixA], 1u);
   return 0u;
 }
 
@@ -421,9 +431,10 @@ template <int PASS, int S>
 __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz,
                                        uint32_t token, uint32_t* colorPx, int pl)
 {
-  const FrameParams& p   = c.p;
-  const size_t       pix = (size_t)yl * p.W + x;
-  const size_t       ai  = ((size_t)sampleID * p.localH + yl) * p.W + x;
+  const FrameParams& p    = c.p;
+  const size_t       pixG = (size_t)yl * p.W + x;            // pixel index in the global images
+  const size_t       pix  = c.onChip ? (size_t)pl : pixG;    // pixel index in the A-buffer slice being used
+  const size_t       ai   = (size_t)sampleID * c.viewSize + pix;
   if(PASS == PASS_LOOP_DEPTH)
   {
     fragLoopDepth(c, pix, sampleID, z);
@@ -439,7 +450,7 @@ __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampl
     case PASS_LOOP64: out = fragLoop64(c, pix, sampleID, rgba, z); break;
     case PASS_SPINLOCK: out = fragLock<true>(c, pix, ai, sampleID, mask, rgba, z); break;
     case PASS_INTERLOCK: out = fragLock<false>(c, pix, ai, sampleID, mask, rgba, z); break;
-    case PASS_WEIGHTED: fragWeighted<S>(c, pix, pl, mask, rgba, viewz); return;
+    case PASS_WEIGHTED: fragWeighted<S>(c, pixG, pl, mask, rgba, viewz); return;
   }
   ropSamples<S>(c, colorPx, mask, out);
 }

@@ -104,11 +104,20 @@ __device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedAr
 }
 
 // the composite invocation of one (pixel, sampleID): returns the colour handed to the ROP
-template <int S>
-__device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, size_t pix,
-                                                           int sampleID)
+// the A-buffer slice the composite reads: the global buffers, or the tile's shared-memory slice of the k-buffer techniques
+struct AbufView
 {
-  const size_t P = (size_t)p.W * p.localH;
+  const uint32_t* abuf;
+  const uint32_t* aux;
+  size_t          viewSize;
+};
+
+// pix: the pixel's index inside that slice
+template <int S>
+__device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, const AbufView& av,
+                                                           size_t pix, int sampleID)
+{
+  const size_t P = av.viewSize;
   const int    L = p.L;
   const size_t ai = (size_t)sampleID * P + pix;
   switch(p.algorithm)
@@ -117,17 +126,17 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
     case OIT_SPINLOCK:
     case OIT_INTERLOCK: {
       const size_t listPos = P * L * sampleID + pix;
-      const int    n       = (int)min((uint32_t)L, p.aux[ai]);
+      const int    n       = (int)min((uint32_t)L, av.aux[ai]);
       for(int i = 0; i < n; i++)
       {
         if(p.coverage)
         {
-          const uint4 e = reinterpret_cast<const uint4*>(p.abuf)[listPos + (size_t)i * P];
+          const uint4 e = reinterpret_cast<const uint4*>(av.abuf)[listPos + (size_t)i * P];
           A.c[i][t] = e.x; A.d[i][t] = e.y; A.m[i][t] = e.z;
         }
         else
         {
-          const uint2 e = reinterpret_cast<const uint2*>(p.abuf)[listPos + (size_t)i * P];
+          const uint2 e = reinterpret_cast<const uint2*>(av.abuf)[listPos + (size_t)i * P];
           A.c[i][t] = e.x; A.d[i][t] = e.y; A.m[i][t] = 0u;
         }
       }
@@ -135,8 +144,8 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
       return fusedBlend<S>(tb, A, t, n, p.coverage != 0);
     }
     case OIT_LINKEDLIST: {
-      const uint4* nodes  = reinterpret_cast<const uint4*>(p.abuf);
-      uint32_t     offset = p.aux[ai];
+      const uint4* nodes  = reinterpret_cast<const uint4*>(av.abuf);
+      uint32_t     offset = av.aux[ai];
       int          n      = 0;
       while(offset != 0u && n < L)
       {
@@ -161,7 +170,7 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
       return out;
     }
     case OIT_LOOP: {
-      const uint32_t* list = p.abuf + P * L * 2 * sampleID + pix;
+      const uint32_t* list = av.abuf + P * L * 2 * sampleID + pix;
       int             n    = 0;
       for(int i = 0; i < L; i++)
       {
@@ -176,7 +185,7 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
       return out;
     }
     case OIT_LOOP64: {
-      const uint2* list = reinterpret_cast<const uint2*>(p.abuf) + P * L * sampleID + pix;
+      const uint2* list = reinterpret_cast<const uint2*>(av.abuf) + P * L * sampleID + pix;
       Color4       out  = zeroColor();
       for(int i = 0; i < L; i++)
       {
@@ -194,8 +203,9 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
 // composite (+ its ROP onto the shared-memory colour tile) of the tile pixel owned by thread t
 // wAcc / wRev: the pixel's S WBOIT accumulator / revealage samples (shared-memory tile), only used for OIT_WEIGHTED
 template <int S>
-__device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, size_t pix, uint32_t* px,
-                                                    const uint2* wAcc = nullptr, const uint16_t* wRev = nullptr)
+__device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, const AbufView& av,
+                                                    size_t pixA, size_t pix, uint32_t* px, const uint2* wAcc = nullptr,
+                                                    const uint16_t* wRev = nullptr)
 {
   if(p.algorithm == OIT_WEIGHTED)
   {
@@ -219,13 +229,13 @@ __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const 
 #pragma unroll 1
     for(int s = 0; s < S; s++)
     {
-      const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, pix, s);
+      const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, av, pixA, s);
       if(!isZero(out))
         px[s] = ropPremult(tb, px[s], out);
     }
     return;
   }
-  const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, pix, 0);
+  const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, av, pixA, 0);
   if(isZero(out))
     return;
   uint32_t prevDst = px[0], prevRes = ropPremult(tb, prevDst, out);

@@ -77,6 +77,7 @@ struct FrameParams
   int      algorithm;   // OIT_*
   int      supersample; // 1 or 2
   int      fused;       // the colour-pass kernel also composites and resolves its tile (oit_render fast path)
+  int      onChip;      // fused only: the tile's A-buffer slice + aux words live in shared memory (k-buffer techniques)
   // tiles
   int tilesX, tileRowsGlobal, tileRowsLocal;
   int stripTileRows, bandCount, bandIndex;
@@ -104,6 +105,24 @@ struct FrameParams
   const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order
   const uint32_t* tileStart;  // [numLocalTiles + 1]
 };
+
+// Fused frame kernel, k-buffer techniques without sample shading: the tile's A-buffer slice and aux words can live in
+// shared memory for the whole pass ("on chip").  Words needed per tile: [A-buffer][imgAux][imgDepth][imgSpin]; 0 = the
+// technique keeps its A-buffer in HBM (linked list: unbounded; Loop32: two geometry passes; WBOIT: no A-buffer).
+__host__ __device__ inline uint32_t onChipAbufWords(int algorithm, int L, int coverage)
+{
+  if(algorithm == OIT_LOOP64)
+    return (uint32_t)TILE_PIX * L * 2u;
+  if(algorithm == OIT_SIMPLE || algorithm == OIT_SPINLOCK || algorithm == OIT_INTERLOCK)
+    return (uint32_t)TILE_PIX * L * (coverage ? 4u : 2u);
+  return 0u;
+}
+__host__ __device__ inline uint32_t onChipWords(int algorithm, int L, int coverage)
+{
+  const uint32_t a = onChipAbufWords(algorithm, L, coverage);
+  return a ? a + 3u * TILE_PIX : 0u;
+}
+constexpr uint32_t ON_CHIP_MAX_BYTES = 36u * 1024u;
 
 __host__ __device__ inline int tileRowOwner(int R, int stripTileRows, int bandCount) { return (R / stripTileRows) % bandCount; }
 __host__ __device__ inline int tileRowToLocal(int R, int stripTileRows, int bandCount)

@@ -216,7 +216,7 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
         const int      px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
         const Bary     b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
         float          vz    = 0.f;
-        const uint32_t token = preInvoke<PASS>(p, gx, yl, (uint32_t)sI);
+        const uint32_t token = preInvoke<PASS>(ctx, ctx.onChip ? (size_t)(ly * TILE_W + lx) : (size_t)yl * p.W + gx, (uint32_t)sI);
         const Color4   rgba  = shadeAt<false>(p, s, b, vz);
         invoke<PASS, S>(ctx, gx, yl, (uint32_t)sI, 1u << sI, rgba, depthAt(s, b), vz, token, colorPx, ly * TILE_W + lx);
       }
@@ -226,7 +226,7 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
     // one invocation per pixel, varyings and gl_FragCoord.z at the pixel centre
     const Bary     bc = makeBary(edgeFloat(s, 1, ox + 128, oy + 128, small), edgeFloat(s, 2, ox + 128, oy + 128, small), s.rarea);
     float          vz    = 0.f;
-    const uint32_t token = preInvoke<PASS>(p, gx, yl, 0u);
+    const uint32_t token = preInvoke<PASS>(ctx, ctx.onChip ? (size_t)(ly * TILE_W + lx) : (size_t)yl * p.W + gx, 0u);
     const Color4   rgba  = shadeAt<PASS == PASS_WEIGHTED>(p, s, bc, vz);
     invoke<PASS, S>(ctx, gx, yl, 0u, mask, rgba, depthAt(s, bc), vz, token, colorPx, ly * TILE_W + lx);
   }
@@ -311,7 +311,30 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   layerCount[1][tid] = 0u;
   if(tid < 2)
     numLayers[tid] = 0u;
-  FragCtx  ctx{p, tabs, 0, 0, 0, 0, (fused && WEIGHTED) ? wAccSm : nullptr, (fused && WEIGHTED) ? wRevSm : nullptr};
+  FragCtx ctx{p, tabs, 0, 0, 0, 0, (fused && WEIGHTED) ? wAccSm : nullptr, (fused && WEIGHTED) ? wRevSm : nullptr,
+              p.abuf, p.aux, p.adepth, p.spin, (size_t)p.W * p.localH, false};
+  if(fused && p.onChip && !WEIGHTED)
+  {
+    // the tile's k-buffer slice + aux words in shared memory, behind the colour tile: [A-buffer][imgAux][imgDepth][imgSpin],
+    // cleared like clearTransparent{Simple,Loop64,Lock} clear the global ones (oitRender.cpp:156-174,303-311,337-356)
+    uint32_t*      base      = reinterpret_cast<uint32_t*>(dynSmem) + TILE_PIX * S;
+    const uint32_t abufWords = onChipAbufWords(p.algorithm, p.L, p.coverage);
+    ctx.abuf     = base;
+    ctx.aux      = base + abufWords;
+    ctx.adepth   = ctx.aux + TILE_PIX;
+    ctx.spin     = ctx.adepth + TILE_PIX;
+    ctx.viewSize = TILE_PIX;
+    ctx.onChip   = true;
+    const uint32_t abufFill = p.algorithm == OIT_LOOP64 ? 0xFFFFFFFFu : 0u;
+    for(uint32_t i = tid; i < abufWords; i += RASTER_THREADS)
+      base[i] = abufFill;
+    for(int i = tid; i < TILE_PIX; i += RASTER_THREADS)
+    {
+      ctx.aux[i]    = 0u;
+      ctx.adepth[i] = 0xFFFFFFFFu;
+      ctx.spin[i]   = 0u;
+    }
+  }
   uint32_t parity = 0;
   const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16), hi = 256 - lo;
   __syncthreads();
@@ -532,8 +555,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
     {
       const int gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
       if(gx < p.W && tileY0 + ly < p.H)
-        fusedCompositePixel<S>(p, tabs, A, pl, (size_t)(yLocal0 + ly) * p.W + gx, tileColorSm + pl * S, WEIGHTED ? wAccSm + pl * S : nullptr,
-                               WEIGHTED ? wRevSm + pl * S : nullptr);
+      {
+        const AbufView av{ctx.abuf, ctx.aux, ctx.viewSize};
+        const size_t   pixG = (size_t)(yLocal0 + ly) * p.W + gx;
+        fusedCompositePixel<S>(p, tabs, A, pl, av, ctx.onChip ? (size_t)pl : pixG, pixG, tileColorSm + pl * S,
+                               WEIGHTED ? wAccSm + pl * S : nullptr, WEIGHTED ? wRevSm + pl * S : nullptr);
+      }
     }
     __syncthreads();
     fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
@@ -559,11 +586,14 @@ static void launchKernel(const FrameParams& p, unsigned grid, cudaStream_t s)
 {
   // eight 128-thread CTAs (eight tiles) per SM need ~160 KB of shared memory: ask for a large carveout once
   // dynamic shared memory of the fused frame kernel: the colour tile, or the RGBA16F + R16F WBOIT tiles (10 B / sample)
-  constexpr size_t dynBytes = (size_t)TILE_PIX * S * (PASS == PASS_WEIGHTED ? 10 : 4);
-  static bool      configured = false;
+  // (+ the tile's k-buffer slice and aux words when the technique runs on chip)
+  const size_t dynBytes = (size_t)TILE_PIX * S * (PASS == PASS_WEIGHTED ? 10 : 4)
+                          + (p.onChip ? (size_t)onChipWords(p.algorithm, p.L, p.coverage) * 4 : 0);
+  static bool configured = false;
   if(!configured)
   {
-    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynBytes);
+    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(TILE_PIX * S * 10 + ON_CHIP_MAX_BYTES));
     if(OIT_SMEM_CARVEOUT >= 0)
       cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
     configured = true;
