@@ -156,7 +156,13 @@ def run_ours(args):
     s.setSceneDevice(dverts.data_ptr(), verts.shape[0], didx.data_ptr(), idx.size, ipo, keepalive=(dverts, didx))
     stream = torch.cuda.ExternalStream(s.L.oit_stream(s.h), device=dev)
     fin_dev = torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
-    band_gather = SF.BandGather(H, W, rank, world, dev, args.strip_rows, torch.int32) if world > 1 else None
+    band_gather = None
+    if world > 1:
+        if args.torch_gather:
+            band_gather = SF.BandGather(H, W, rank, world, dev, args.strip_rows, torch.int32)   # gather driven from Python
+        else:
+            s.enableBandGather(dist)   # default: the band gather is part of the library's frame graph
+            fin_dev = torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
     hfinal = torch.empty((s.localRows, W), dtype=torch.int32).pin_memory()
 
     def barrier():
@@ -170,14 +176,14 @@ def run_ours(args):
             band_gather.gather(fin_dev)
 
     def step_resident():
-        s.onRender(ubo)                      # the strips of this band are complete on the device when this returns
-        if world > 1:
+        s.onRender(ubo)                      # render (+ in-library band gather): complete on the device when this returns
+        if band_gather is not None:
             gather()
 
     def step_e2e():
         s.setScene(hverts.numpy(), hidx.numpy().view(np.uint32), ipo)   # H2D of the step's inputs from pinned memory
         s.onRender(ubo)
-        if world > 1:
+        if band_gather is not None:
             gather()
         s.readColor(hfinal.numpy().view(np.uint32))                      # D2H of the step's result
 
@@ -213,6 +219,20 @@ def run_ours(args):
         return t[0].item(), t[1].item(), {k: v / steps for k, v in stage.items()}, launches, clocks, sst
 
     ms_total, wall_total, stage_ms, launches, clocks, last = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    gather_ok = None
+    if world > 1 and band_gather is None:
+        # untimed check of the in-library band gather: this rank's strips sit on the right rows of the gathered frame and
+        # every rank holds the same frame
+        frame = torch.as_tensor(s.frameDevice(), device=dev)
+        rows = torch.as_tensor(SF.band_rows(H, world, rank, args.strip_rows), device=dev)
+        mine_ok = bool(torch.equal(frame[rows], fin_dev))
+        chk = frame.to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        okt = torch.tensor([1 if (mine_ok and lo.item() == hi.item()) else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_ok = bool(okt.item())
     F_local = last["fragments"]
     Ft = torch.tensor([F_local, last["fragmentsStored"], last["fragmentsTail"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -252,6 +272,8 @@ def run_ours(args):
             "data": "synthetic (the sample's seeded sphere cloud, generated on the host)",
             "config": {"workload": f"{args.workload}: {desc}", "fragments_per_frame": F, "fragments_stored": Fst, "fragments_tail": Ftb,
                        "width": W, "height": H, "parallelism": f"split-frame x{world}, {args.strip_rows}-row interleaved strips" if world > 1 else "single GPU",
+                       "band_gather": None if world == 1 else ("torch.distributed all_gather" if band_gather is not None else "in-library ncclAllGather inside the frame graph"),
+                       "band_gather_verified": gather_ok,
                        "l2_policy": "working set (A-buffer + colour samples) is larger than L2; no explicit flush"},
             "ms_per_frame": frame_ms, "wall_ms_per_frame": wall_total / args.steps, "stages": per_stage, "gpu_launches": int(launches),
             "e2e": {"value": F / (e2e_ms * 1e-3), "unit": "fragments/s", "ms_per_step": e2e_ms,
@@ -361,6 +383,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--strip-rows", type=int, default=32)
+    ap.add_argument("--torch-gather", action="store_true", help="N>1: drive the band gather from Python (torch.distributed) instead of the library's frame graph")
     ap.add_argument("--no-table", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

@@ -136,7 +136,8 @@ typedef enum OitBuffer
   OIT_BUF_DEPTH    = 6, /* m_depthImage: float [y][x][sample]; only allocated when something opaque is drawn */
   OIT_BUF_WACCUM   = 7, /* WBOIT RGBA16F [y][x][sample][4] */
   OIT_BUF_WREVEAL  = 8, /* WBOIT R16F   [y][x][sample] */
-  OIT_BUF_FINAL    = 9  /* m_viewportImage: BGRA8, width x (rows owned by this band), sRGB-encoded bytes */
+  OIT_BUF_FINAL    = 9, /* m_viewportImage: BGRA8, width x (rows owned by this band), sRGB-encoded bytes */
+  OIT_BUF_FRAME    = 10 /* split frame with the band gather enabled: the whole m_viewportImage, width x height, on every rank */
 } OitBuffer;
 
 typedef struct OitCtx OitCtx;
@@ -190,6 +191,15 @@ int   oit_get_stats(OitCtx* ctx, OitStats* out);
 void* oit_stream(OitCtx* ctx);             /* the cudaStream_t the context launches on */
 /* global row index of local row r of this band (for reassembling the gathered strips) */
 int   oit_local_row_to_global(const OitCtx* ctx, uint32_t localRow, uint32_t* globalRow);
+
+/* ---- split frame: band gather inside the library (no reference counterpart: the sample is single GPU) -------------------
+   One process per GPU, each with a context created with bandCount = world size and bandIndex = rank.  Rank 0 calls
+   oit_band_gather_unique_id and distributes the 128 bytes (any host transport; the Python mirror uses torch.distributed);
+   then EVERY rank calls oit_enable_band_gather (collective).  From then on oit_render ends with ONE ncclAllGather over
+   NVLink of the resolved strips (in place) + the row interleave, captured into the frame graph, and OIT_BUF_FRAME holds
+   the whole frame on every rank.  width must be a multiple of 4.  NCCL is loaded with dlopen("libnccl.so.2"). */
+int oit_band_gather_unique_id(void* id128);
+int oit_enable_band_gather(OitCtx* ctx, const void* id128);
 
 #ifdef __cplusplus
 }

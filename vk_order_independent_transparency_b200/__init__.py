@@ -29,7 +29,9 @@ ABI_SYMBOLS = [
     "oit_default_camera", "oit_render", "oit_set_scene_data", "oit_begin_frame", "oit_draw_opaque",
     "oit_draw_transparent", "oit_composite", "oit_resolve", "oit_synchronize", "oit_buffer_size", "oit_download",
     "oit_upload", "oit_device_ptr", "oit_read_color", "oit_get_stats", "oit_stream", "oit_local_row_to_global",
+    "oit_band_gather_unique_id", "oit_enable_band_gather",
 ]
+BUF_FRAME = 10
 
 
 class OitError(RuntimeError):
@@ -110,6 +112,8 @@ def load_library():
     L.oit_stream.argtypes = [vp]
     L.oit_stream.restype = vp
     L.oit_local_row_to_global.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.oit_band_gather_unique_id.argtypes = [vp]
+    L.oit_enable_band_gather.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -354,6 +358,30 @@ class Sample:
         s = OitStats()
         self._check(self.L.oit_get_stats(self.h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in OitStats._fields_}
+
+    def enableBandGather(self, dist=None):
+        """Split frame: make onRender end with the in-library band gather (ONE ncclAllGather + row interleave inside the
+        frame graph).  Collective over the bandCount ranks; `dist` = an initialised torch.distributed (any backend), used
+        only to hand rank 0's 128-byte NCCL id to the other ranks.  Afterwards frameDevice() is the whole frame."""
+        import torch
+        ident = (C.c_ubyte * 128)()
+        if self.cfg.bandIndex == 0:
+            self._check(self.L.oit_band_gather_unique_id(ident))
+        if self.cfg.bandCount > 1:
+            if dist is None:
+                import torch.distributed as dist
+            box = [bytes(ident)]
+            dist.broadcast_object_list(box, src=0)
+            ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._check(self.L.oit_enable_band_gather(self.h, ident))
+
+    def frameDevice(self):
+        """The gathered full frame (uint32 BGRA8 [height, width]) as a __cuda_array_interface__ object (zero copy)."""
+        ptr = self.L.oit_device_ptr(self.h, BUF_FRAME)
+        return _DeviceArray(ptr, (self.height, self.width), "<i4", self) if ptr else None
+
+    def readFrame(self):
+        return self.download(BUF_FRAME).reshape(self.height, self.width)
 
     def localRowToGlobal(self, r):
         g = C.c_uint32()

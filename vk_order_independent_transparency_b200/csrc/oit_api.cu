@@ -92,6 +92,13 @@ struct OitCtx
   bool            fuseFrame  = false;  // oit_render: colour pass + composite + resolve in one kernel
   unsigned long long* hostMirror  = nullptr;  // pinned: statistics + pair counts copied back by the frame itself
   bool                mirrorValid = false;
+  // split frame: band gather inside the library (oit_gather.cu)
+  BandGatherState* gather     = nullptr;
+  DevBuf           gatherBuf, frame;
+  uint32_t         padRows    = 0;
+  bool             gatherWarm = false;  // NCCL has run once outside a capture (connection set-up must not be captured)
+  bool             skipGather = false;  // re-render after a buffer growth: the frame's one collective already ran
+  bool             finOwned   = true;   // false once `fin` is this rank's slice of the gather buffer
   uint64_t        graphLaunches = 0;
   int        sortedBuf[2]{};
   uint32_t*  hostScalar = nullptr;  // pinned
@@ -211,6 +218,7 @@ DevBuf* bufferOf(OitCtx* c, OitBuffer which)
     case OIT_BUF_WACCUM: return &c->wacc;
     case OIT_BUF_WREVEAL: return &c->wrev;
     case OIT_BUF_FINAL: return &c->fin;
+    case OIT_BUF_FRAME: return &c->frame;
   }
   return nullptr;
 }
@@ -520,8 +528,18 @@ int oit_destroy(OitCtx* c)
   cudaSetDevice(c->cfg.device);
   if(c->stream)
     cudaStreamSynchronize(c->stream);
+  // the captured frame graph references the NCCL communicator: it has to go first
+  if(c->graphExec)
+    cudaGraphExecDestroy(c->graphExec);
+  if(c->graph)
+    cudaGraphDestroy(c->graph);
+  c->graphExec = nullptr;
+  c->graph     = nullptr;
+  gatherDestroy(c->gather);
+  if(!c->finOwned)
+    c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
-                   &c->tables, &c->stats, &c->tv})
+                   &c->tables, &c->stats, &c->tv, &c->gatherBuf, &c->frame})
     devFree(*b);
   if(c->sceneOwned)
   {
@@ -815,6 +833,15 @@ static int issueFrame(OitCtx* c)
     return r;
   if((r = oit_resolve(c)) != OIT_OK)
     return r;
+  // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
+  if(c->gather && !c->skipGather)
+  {
+    const int n = gatherLaunch(c->gather, (uint32_t*)c->gatherBuf.p, (uint32_t*)c->frame.p, (int)c->cfg.width, (int)c->cfg.height,
+                               (int)c->stripRows, (int)c->padRows, c->stream, c->error);
+    if(n < 0)
+      return n;
+    c->launches += n;
+  }
   // mirror the statistics and the pair counts into pinned host memory as the last nodes of the frame
   CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror, c->stats.p, NUM_STAT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   for(int which = 0; which < 2; which++)
@@ -851,7 +878,8 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
                          ? 1
                          : 0;
     }
-    if(c->useGraph)
+    // (with the band gather, the first frame runs un-captured so that NCCL sets up its connections outside a capture)
+    if(c->useGraph && (!c->gather || c->gatherWarm))
     {
       // the whole frame (~30 kernels) is captured once and replayed as one graph launch
       if(!c->graphValid)
@@ -907,6 +935,20 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     c->mirrorValid = false;
     if(r != OIT_OK)
       return r;
+    if(c->gather)
+    {
+      c->gatherWarm = true;
+      if(c->skipGather)
+      {
+        // this was the re-render after a pair-buffer growth: the collective already ran (once per oit_render on every
+        // rank, or the ranks would deadlock), so the other ranks keep this band's strips of the overflowed attempt for
+        // this one frame.  Only happens on the first frame(s) after a scene / camera change that needs larger buffers.
+        c->skipGather = false;
+        c->graphValid = false;
+      }
+      else if(grown)
+        c->skipGather = true;
+    }
     if(!grown)
       return OIT_OK;
   }
@@ -1009,6 +1051,60 @@ void* oit_device_ptr(OitCtx* c, OitBuffer which)
 int oit_read_color(OitCtx* c, void* bgra8, size_t bytes) { return oit_download(c, OIT_BUF_FINAL, bgra8, bytes); }
 
 void* oit_stream(OitCtx* c) { return c ? (void*)c->stream : nullptr; }
+
+int oit_band_gather_unique_id(void* id128)
+{
+  if(!id128)
+    return OIT_ERR_INVALID_ARG;
+  std::string err;
+  const int   r = gatherUniqueId(id128, err);
+  if(r != OIT_OK)
+    g_createError = err;
+  return r;
+}
+
+int oit_enable_band_gather(OitCtx* c, const void* id128)
+{
+  if(!c || !id128)
+    return OIT_ERR_INVALID_ARG;
+  if(c->gather)
+    return OIT_OK;
+  if(c->cfg.width % 4)
+    return fail(c, OIT_ERR_INVALID_ARG, "the band gather needs a width that is a multiple of 4");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // rows of the largest band: every rank contributes a slice of that many (padded) rows
+  uint32_t pad = 0;
+  for(uint32_t b = 0; b < c->cfg.bandCount; b++)
+  {
+    uint32_t rows = 0;
+    for(uint32_t y0 = 0; y0 < c->cfg.height; y0 += c->stripRows)
+      if((y0 / c->stripRows) % c->cfg.bandCount == b)
+        rows += std::min(c->stripRows, c->cfg.height - y0);
+    pad = std::max(pad, rows);
+  }
+  c->padRows = pad;
+  const size_t slice = (size_t)pad * c->cfg.width;
+  int          r;
+  if((r = devAlloc(c, c->gatherBuf, slice * c->cfg.bandCount * 4)) != OIT_OK)
+    return r;
+  if((r = devAlloc(c, c->frame, (size_t)c->cfg.width * c->cfg.height * 4)) != OIT_OK)
+    return r;
+  CUDA_TRY(c, cudaMemset(c->gatherBuf.p, 0, c->gatherBuf.bytes));
+  c->gather = gatherCreate(id128, (int)c->cfg.bandIndex, (int)c->cfg.bandCount, c->error);
+  if(!c->gather)
+    return OIT_ERR_CUDA;
+  // the resolve now writes straight into this rank's slice of the gather buffer (in-place all-gather)
+  if(c->finOwned)
+    devFree(c->fin);
+  c->finOwned   = false;
+  c->fin.p      = (uint32_t*)c->gatherBuf.p + slice * c->cfg.bandIndex;
+  c->fin.bytes  = std::max<size_t>((size_t)c->cfg.width * c->localOutH, 1) * 4;
+  c->fp.fin     = (uint32_t*)c->fin.p;
+  c->graphValid = false;
+  c->gatherWarm = false;
+  return OIT_OK;
+}
 
 int oit_local_row_to_global(const OitCtx* c, uint32_t localRow, uint32_t* globalRow)
 {

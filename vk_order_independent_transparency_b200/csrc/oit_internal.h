@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/oit_b200.h"
 
 namespace oit {
@@ -153,6 +155,14 @@ struct BinBuffers
 int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
               cudaStream_t s);
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
+
+// band gather of the split-frame mode (oit_gather.cu); NCCL is loaded lazily with dlopen
+struct BandGatherState;
+int              gatherUniqueId(void* id128, std::string& err);
+BandGatherState* gatherCreate(const void* id128, int rank, int world, std::string& err);
+void             gatherDestroy(BandGatherState* g);
+int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, cudaStream_t s,
+                 std::string& err);
 
 int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s);
