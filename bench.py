@@ -156,13 +156,16 @@ def run_ours(args):
     s.setSceneDevice(dverts.data_ptr(), verts.shape[0], didx.data_ptr(), idx.size, ipo, keepalive=(dverts, didx))
     stream = torch.cuda.ExternalStream(s.L.oit_stream(s.h), device=dev)
     fin_dev = torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
-    band_gather = None
+    band_gather, exchange = None, None
     if world > 1:
         if args.torch_gather:
             band_gather = SF.BandGather(H, W, rank, world, dev, args.strip_rows, torch.int32)   # gather driven from Python
+        elif not args.nccl_gather and s.enableBandPeers(dist):
+            exchange = "peer memory: the frame kernel stores every resolved pixel into all bands' frame buffers over NVLink (CUDA IPC), 2 flag rounds per frame inside the frame graph"
         else:
-            s.enableBandGather(dist)   # default: the band gather is part of the library's frame graph
-            fin_dev = torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
+            s.enableBandGather(dist)   # the band gather as ONE ncclAllGather + interleave at the end of the frame graph
+            exchange = "in-library ncclAllGather inside the frame graph"
+            fin_dev =torch.as_tensor(s.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: s.localRows * W].view(s.localRows, W)
     hfinal = torch.empty((s.localRows, W), dtype=torch.int32).pin_memory()
 
     def barrier():
@@ -272,7 +275,7 @@ def run_ours(args):
             "data": "synthetic (the sample's seeded sphere cloud, generated on the host)",
             "config": {"workload": f"{args.workload}: {desc}", "fragments_per_frame": F, "fragments_stored": Fst, "fragments_tail": Ftb,
                        "width": W, "height": H, "parallelism": f"split-frame x{world}, {args.strip_rows}-row interleaved strips" if world > 1 else "single GPU",
-                       "band_gather": None if world == 1 else ("torch.distributed all_gather" if band_gather is not None else "in-library ncclAllGather inside the frame graph"),
+                       "band_gather": None if world == 1 else ("torch.distributed all_gather" if band_gather is not None else exchange),
                        "band_gather_verified": gather_ok,
                        "l2_policy": "working set (A-buffer + colour samples) is larger than L2; no explicit flush"},
             "ms_per_frame": frame_ms, "wall_ms_per_frame": wall_total / args.steps, "stages": per_stage, "gpu_launches": int(launches),
@@ -383,6 +386,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--strip-rows", type=int, default=32)
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: exchange the strips with the in-library ncclAllGather instead of peer-memory stores")
     ap.add_argument("--torch-gather", action="store_true", help="N>1: drive the band gather from Python (torch.distributed) instead of the library's frame graph")
     ap.add_argument("--no-table", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -201,6 +201,19 @@ int   oit_local_row_to_global(const OitCtx* ctx, uint32_t localRow, uint32_t* gl
 int oit_band_gather_unique_id(void* id128);
 int oit_enable_band_gather(OitCtx* ctx, const void* id128);
 
+/* ---- split frame over NVLink peer memory (preferred; same contexts as above, no reference counterpart) ----------------
+   Every band owns a whole-frame buffer (OIT_BUF_FRAME).  oit_band_peer_export allocates it and returns its CUDA IPC handle
+   (64 bytes); the host gathers the handles of all bands in band order (any transport) and passes them to
+   oit_band_peer_enable, which maps the other bands' buffers.  From then on the frame kernel of oit_render stores every
+   resolved pixel straight into ALL bands' frame buffers while it renders (no collective after the frame), and two flag
+   rounds per frame (device-side sequence numbers, part of the frame graph) keep the bands in step; OIT_BUF_FRAME holds
+   the whole frame on every band when oit_render returns.  Every band must call oit_render the same number of times.
+   Tear-down: all bands finish rendering, host barrier, oit_band_peer_disable on every band, host barrier, oit_destroy.
+   Returns OIT_ERR_UNSUPPORTED when the devices cannot map each other's memory (fall back to the NCCL gather above). */
+int oit_band_peer_export(OitCtx* ctx, void* handle64);
+int oit_band_peer_enable(OitCtx* ctx, const void* handles, uint32_t count);
+int oit_band_peer_disable(OitCtx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

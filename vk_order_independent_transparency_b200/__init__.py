@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
     "oit_default_camera", "oit_render", "oit_set_scene_data", "oit_begin_frame", "oit_draw_opaque",
     "oit_draw_transparent", "oit_composite", "oit_resolve", "oit_synchronize", "oit_buffer_size", "oit_download",
     "oit_upload", "oit_device_ptr", "oit_read_color", "oit_get_stats", "oit_stream", "oit_local_row_to_global",
-    "oit_band_gather_unique_id", "oit_enable_band_gather",
+    "oit_band_gather_unique_id", "oit_enable_band_gather", "oit_band_peer_export", "oit_band_peer_enable",
+    "oit_band_peer_disable",
 ]
 BUF_FRAME = 10
 
@@ -114,6 +115,9 @@ def load_library():
     L.oit_local_row_to_global.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.oit_band_gather_unique_id.argtypes = [vp]
     L.oit_enable_band_gather.argtypes = [vp, vp]
+    L.oit_band_peer_export.argtypes = [vp, vp]
+    L.oit_band_peer_enable.argtypes = [vp, vp, C.c_uint32]
+    L.oit_band_peer_disable.argtypes = [vp]
     _lib = L
     return L
 
@@ -220,6 +224,14 @@ class Sample:
     # ---- lifetime -----------------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "h", None):
+            dist = getattr(self, "_peer_dist", None)
+            if dist is not None:
+                # peer-memory split frame: nobody may still store into a buffer that is about to be unmapped / freed
+                self._peer_dist = None
+                self.L.oit_synchronize(self.h)
+                dist.barrier()
+                self.L.oit_band_peer_disable(self.h)
+                dist.barrier()
             self.L.oit_destroy(self.h)
             self.h = None
 
@@ -374,6 +386,32 @@ class Sample:
             dist.broadcast_object_list(box, src=0)
             ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
         self._check(self.L.oit_enable_band_gather(self.h, ident))
+
+    def enableBandPeers(self, dist=None):
+        """Split frame over NVLink peer memory: the frame kernel of onRender stores its resolved pixels straight into the
+        frame buffer of EVERY band (CUDA IPC mappings), two flag rounds per frame keep the bands in step.  Collective over
+        the bandCount ranks; `dist` = an initialised torch.distributed, used only to exchange the 64-byte IPC handles.
+        Returns False (on every rank, nothing enabled) when some rank cannot map its peers: use enableBandGather then."""
+        if dist is None:
+            import torch.distributed as dist
+        world = max(self.cfg.bandCount, 1)
+        handle = (C.c_ubyte * 64)()
+        ok = self.L.oit_band_peer_export(self.h, handle) == 0
+        box = [None] * world
+        dist.all_gather_object(box, (ok, bytes(handle)))
+        ok = all(b[0] for b in box)
+        if ok:
+            blob = b"".join(b[1] for b in box)
+            ok = self.L.oit_band_peer_enable(self.h, (C.c_ubyte * len(blob)).from_buffer_copy(blob), world) == 0
+        box = [None] * world
+        dist.all_gather_object(box, ok)
+        if all(box):
+            self._peer_dist = dist
+            return True
+        self.L.oit_band_peer_disable(self.h)  # unmap whatever was mapped ...
+        dist.barrier()
+        self.L.oit_band_peer_disable(self.h)  # ... then release the exported buffer
+        return False
 
     def frameDevice(self):
         """The gathered full frame (uint32 BGRA8 [height, width]) as a __cuda_array_interface__ object (zero copy)."""

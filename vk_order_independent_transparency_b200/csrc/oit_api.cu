@@ -99,6 +99,9 @@ struct OitCtx
   bool             gatherWarm = false;  // NCCL has run once outside a capture (connection set-up must not be captured)
   bool             skipGather = false;  // re-render after a buffer growth: the frame's one collective already ran
   bool             finOwned   = true;   // false once `fin` is this rank's slice of the gather buffer
+  // split frame over peer memory (oit_peer.cu): the frame kernel stores into every band's frame buffer
+  PeerState* peers     = nullptr;
+  bool       peersOpen = false;
   uint64_t        graphLaunches = 0;
   int        sortedBuf[2]{};
   uint32_t*  hostScalar = nullptr;  // pinned
@@ -156,6 +159,12 @@ void freeBins(BinBuffers& b)
   cudaFree(b.tileStart);
   cudaFree(b.pairInfo);
   cudaFree(b.scratch);
+  for(int i = 0; i < 2; i++)
+  {
+    cudaFree(b.tileKey[i]);
+    cudaFree(b.tileOrder[i]);
+  }
+  cudaFree(b.tileScratch);
   b = BinBuffers{};
 }
 
@@ -174,8 +183,14 @@ int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
     CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
   }
   CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 2 * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 2 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 4 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 4 * sizeof(uint32_t)));
+  for(int i = 0; i < 2; i++)
+  {
+    CUDA_TRY(c, cudaMalloc(&b.tileKey[i], std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
+    CUDA_TRY(c, cudaMalloc(&b.tileOrder[i], std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
+  }
+  CUDA_TRY(c, cudaMalloc(&b.tileScratch, tileScratchWords(numTiles) * sizeof(uint32_t)));
   CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
   c->graphValid = false;  // the captured frame refers to the old buffers
   return OIT_OK;
@@ -274,6 +289,7 @@ void useBins(OitCtx* c, int which)
 {
   c->fp.pairTri   = c->bins[which].pairVal[c->sortedBuf[which]];
   c->fp.tileStart = c->bins[which].tileStart;
+  c->fp.tileOrder = c->bins[which].tileOrder[0];
 }
 
 int ensureSceneBins(OitCtx* c)
@@ -536,6 +552,11 @@ int oit_destroy(OitCtx* c)
   c->graphExec = nullptr;
   c->graph     = nullptr;
   gatherDestroy(c->gather);
+  if(c->peers)
+  {
+    peerDestroy(c->peers);
+    c->frame = DevBuf{};  // part of the peer chunk
+  }
   if(!c->finOwned)
     c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
@@ -822,17 +843,38 @@ int oit_synchronize(OitCtx* c)
 // every stage of one frame, asynchronously on the context's stream
 static int issueFrame(OitCtx* c)
 {
-  int r;
+  int        r;
+  const bool exchange = c->peers && c->peersOpen;
+  // split frame over peer memory: "my frame buffer may be overwritten" goes out first, the wait for the other bands'
+  // comes as late as possible (the geometry stage and the opaque pass absorb the skew between the bands)
+  if(exchange && !c->skipGather)
+    c->launches += peerSignal(c->peers, PEER_FLAG_READY, c->stream);
   if((r = oit_begin_frame(c)) != OIT_OK)
     return r;
   if((r = oit_draw_opaque(c)) != OIT_OK)
     return r;
-  if((r = oit_draw_transparent(c)) != OIT_OK)
+  if(exchange && !c->skipGather)
+    c->launches += peerWait(c->peers, PEER_FLAG_READY, (unsigned long long*)c->stats.p, c->stream);
+  c->fp.peers = (exchange && c->fp.fused) ? peerTable(c->peers) : nullptr;  // the fused kernel stores to every band
+  r           = oit_draw_transparent(c);
+  c->fp.peers = nullptr;
+  if(r != OIT_OK)
     return r;
   if((r = oit_composite(c)) != OIT_OK)
     return r;
   if((r = oit_resolve(c)) != OIT_OK)
     return r;
+  if(exchange)
+  {
+    if(!c->fp.fused)
+      c->launches += peerScatterRows(c->peers, (const uint32_t*)c->fin.p, (int)c->cfg.width, (int)c->localOutH, (int)c->stripRows, c->stream);
+    if(!c->skipGather)
+    {
+      c->launches += peerSignal(c->peers, PEER_FLAG_DONE, c->stream);
+      c->launches += peerWait(c->peers, PEER_FLAG_DONE, (unsigned long long*)c->stats.p, c->stream);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+  }
   // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
   if(c->gather && !c->skipGather)
   {
@@ -935,7 +977,9 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     c->mirrorValid = false;
     if(r != OIT_OK)
       return r;
-    if(c->gather)
+    if(c->hostMirror[STAT_PEER_TIMEOUT] != 0)
+      return fail(c, OIT_ERR_CUDA, "split frame: a band did not reach the frame barrier (peer exchange timed out)");
+    if(c->gather || (c->peers && c->peersOpen))
     {
       c->gatherWarm = true;
       if(c->skipGather)
@@ -1069,6 +1113,8 @@ int oit_enable_band_gather(OitCtx* c, const void* id128)
     return OIT_ERR_INVALID_ARG;
   if(c->gather)
     return OIT_OK;
+  if(c->peers)
+    return fail(c, OIT_ERR_INVALID_ARG, "the peer-memory exchange is already enabled on this context");
   if(c->cfg.width % 4)
     return fail(c, OIT_ERR_INVALID_ARG, "the band gather needs a width that is a multiple of 4");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
@@ -1103,6 +1149,68 @@ int oit_enable_band_gather(OitCtx* c, const void* id128)
   c->fp.fin     = (uint32_t*)c->fin.p;
   c->graphValid = false;
   c->gatherWarm = false;
+  return OIT_OK;
+}
+
+int oit_band_peer_export(OitCtx* c, void* handle64)
+{
+  if(!c || !handle64)
+    return OIT_ERR_INVALID_ARG;
+  if(c->gather)
+    return fail(c, OIT_ERR_INVALID_ARG, "the NCCL band gather is already enabled on this context");
+  if(c->cfg.width % 4)
+    return fail(c, OIT_ERR_INVALID_ARG, "the split-frame exchange needs a width that is a multiple of 4");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(c->peers)
+    return fail(c, OIT_ERR_INVALID_ARG, "oit_band_peer_export has already been called");
+  const size_t bytes = (size_t)c->cfg.width * c->cfg.height * 4;
+  c->peers           = peerCreate((int)c->cfg.bandIndex, (int)c->cfg.bandCount, bytes, handle64, c->error);
+  if(!c->peers)
+    return OIT_ERR_UNSUPPORTED;
+  devFree(c->frame);
+  c->frame.p     = peerFrame(c->peers);
+  c->frame.bytes = bytes;
+  return OIT_OK;
+}
+
+int oit_band_peer_enable(OitCtx* c, const void* handles, uint32_t count)
+{
+  if(!c || !handles)
+    return OIT_ERR_INVALID_ARG;
+  if(!c->peers || count != c->cfg.bandCount)
+    return fail(c, OIT_ERR_INVALID_ARG, "oit_band_peer_enable: call oit_band_peer_export first and pass one handle per band");
+  if(c->peersOpen)
+    return OIT_OK;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const int r = peerOpen(c->peers, handles, c->error);
+  if(r != OIT_OK)
+    return r;
+  c->peersOpen  = true;
+  c->graphValid = false;
+  c->skipGather = false;
+  return OIT_OK;
+}
+
+int oit_band_peer_disable(OitCtx* c)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  if(!c->peers)
+    return OIT_OK;
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->graphValid = false;
+  if(c->peersOpen)
+  {
+    peerClose(c->peers);  // first call: the other bands' buffers are unmapped
+    c->peersOpen = false;
+    return OIT_OK;
+  }
+  peerDestroy(c->peers);  // second call (or export only): the exported buffer itself goes
+  c->peers = nullptr;
+  c->frame = DevBuf{};
   return OIT_OK;
 }
 

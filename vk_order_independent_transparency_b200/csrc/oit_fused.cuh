@@ -291,6 +291,15 @@ __device__ __forceinline__ void fusedResolveTile(const FrameParams& p, const Srg
       result = encodeDst(tb, Color4{__fmul_rn(sum[0], inv), __fmul_rn(sum[1], inv), __fmul_rn(sum[2], inv), __fmul_rn(sum[3], inv)});
     }
     p.fin[(size_t)gy * outW + gx] = result;
+    if(p.peers)
+    {
+      // split frame over peer memory: the pixel goes straight into every band's whole-frame buffer (NVLink stores)
+      const int    stripRows = p.stripTileRows * TILE_H / ss;
+      const int    strip     = gy / stripRows;
+      const size_t o         = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (gy - strip * stripRows)) * outW + gx;
+      for(int b = 0; b < p.bandCount; b++)
+        p.peers->frame[b][o] = result;
+    }
   }
 }
 

@@ -341,6 +341,51 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
   }
 }
 
+// heavy tiles first: key = ~(triangles in the tile's list), so that the ascending sort puts the longest lists at the front
+// of the launch order and the light tiles fill the tail of the grid (longest-processing-time-first scheduling)
+__global__ void __launch_bounds__(256) k_tile_cost(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ nOut)
+{
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    *nOut = numTiles;
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x)
+  {
+    const uint32_t n = min(tileStart[t + 1] - tileStart[t], 0xFFFFu);
+    keys[t]          = 0xFFFFu - n;
+    vals[t]          = t;
+  }
+}
+
+// tileOrder = tile indices sorted by decreasing list length; returns the kernels launched, *sortedBuf = which buffer
+static int launchTileOrder(const BinBuffers& b, uint32_t numTiles, cudaStream_t s)
+{
+  if(numTiles == 0)
+    return 0;
+  const int blocks = (int)min((numTiles + 255u) / 256u, 148u * 4u);
+  k_tile_cost<<<blocks, 256, 0, s>>>(b.tileStart, numTiles, b.tileKey[0], b.tileOrder[0], b.pairInfo + 2);
+  int            launches = 1;
+  const uint32_t nb       = (numTiles + SORT_TILE - 1) / SORT_TILE;
+  uint32_t*      table    = b.tileScratch;
+  uint32_t*      tscan    = table + (size_t)256 * nb + 1;
+  int            cur      = 0;
+  for(int shift = 0; shift < 16; shift += 8)
+  {
+    k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.tileKey[cur], b.pairInfo + 2, shift, table, nb);
+    launches += 1 + launchScan(table, table, (size_t)256 * nb, tscan, s);
+    k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.tileKey[cur], b.tileOrder[cur], b.tileKey[cur ^ 1], b.tileOrder[cur ^ 1], b.pairInfo + 2, shift,
+                                               table, nb);
+    launches++;
+    cur ^= 1;
+  }
+  return launches;  // two passes: the sorted order is back in tileOrder[0]
+}
+size_t tileScratchWords(size_t numTiles)
+{
+  const size_t nb    = (numTiles + SORT_TILE - 1) / SORT_TILE;
+  const size_t table = 256 * nb + 1;
+  return table + scanBlocks(table) + 2;
+}
+
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t /*numTiles*/)
 {
   const size_t sortBlocks = (pairCapacity + SORT_TILE - 1) / SORT_TILE;
@@ -388,6 +433,7 @@ int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint
   k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], b.pairInfo, numTiles, b.tileStart);
   launches++;
   *sortedBuf = cur;
+  launches += launchTileOrder(b, numTiles, s);
   return launches;
 }
 

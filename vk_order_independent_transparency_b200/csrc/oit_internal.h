@@ -55,7 +55,21 @@ enum StatSlot
   STAT_OPAQUE,
   STAT_REJECTED,
   STAT_OVERFLOW,  // the (tile, triangle) pair buffer of a draw was too small: the frame must be rendered again
+  STAT_PEER_TIMEOUT,  // split frame over peer memory: a band did not arrive at the frame barrier in time
   NUM_STAT_SLOTS = 8
+};
+
+// Split frame over NVLink peer memory (oit_peer.cu): band b's resolved pixels are stored straight into the whole-frame
+// buffer of every band (its own included) by the kernel that produces them.
+constexpr int PEER_MAX       = 16;
+constexpr int PEER_FLAG_READY = 0;             // flags[READY + b] = n: band b no longer reads frame n - 1 of ITS buffer
+constexpr int PEER_FLAG_DONE  = PEER_MAX;      // flags[DONE + b]  = n: band b's strips of frame n are in THIS buffer
+constexpr int PEER_FLAG_SEQ   = 2 * PEER_MAX;  // frames completed by this band (local use)
+constexpr int PEER_FLAG_WORDS = 64;
+struct PeerTable
+{
+  uint32_t* frame[PEER_MAX];  // whole frame [H][W] BGRA8 of band b (peer-mapped, own entry local)
+  uint32_t* flags[PEER_MAX];  // PEER_FLAG_WORDS words next to it
 };
 
 struct DeviceUbo
@@ -96,6 +110,7 @@ struct FrameParams
   uint16_t*            wacc;
   uint16_t*            wrev;
   uint32_t*            fin;
+  const PeerTable*     peers;   // split frame over peer memory: every band's whole-frame buffer (nullptr = off)
   const float*         tables;  // [0,256): sRGB8 -> linear, [256,512): encode thresholds, [512,768): v/255
   unsigned long long*  stats;
   // geometry
@@ -106,6 +121,7 @@ struct FrameParams
   // binning of the current draw
   const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order
   const uint32_t* tileStart;  // [numLocalTiles + 1]
+  const uint32_t* tileOrder;  // [numLocalTiles] tile handled by CTA i: heaviest triangle lists first
 };
 
 // Fused frame kernel, k-buffer techniques without sample shading: the tile's A-buffer slice and aux words can live in
@@ -146,7 +162,10 @@ struct BinBuffers
   uint32_t* pairKey[2];  // [pairCapacity]
   uint32_t* pairVal[2];
   uint32_t* tileStart;   // [numLocalTiles + 1]
-  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics)
+  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics), [2] tiles
+  uint32_t* tileKey[2];  // [numLocalTiles] launch order of the tiles: heaviest lists first (tileOrder[0] after launchBin)
+  uint32_t* tileOrder[2];
+  uint32_t* tileScratch;
   uint32_t* scratch;     // scan / histogram scratch
   size_t    scratchWords;
   size_t    pairCapacity;
@@ -155,6 +174,7 @@ struct BinBuffers
 int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
               cudaStream_t s);
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
+size_t tileScratchWords(size_t numTiles);
 
 // band gather of the split-frame mode (oit_gather.cu); NCCL is loaded lazily with dlopen
 struct BandGatherState;
@@ -163,6 +183,18 @@ BandGatherState* gatherCreate(const void* id128, int rank, int world, std::strin
 void             gatherDestroy(BandGatherState* g);
 int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, cudaStream_t s,
                  std::string& err);
+
+// split frame over peer memory (oit_peer.cu): CUDA IPC mappings of every band's frame buffer + flag barrier kernels
+struct PeerState;
+PeerState*       peerCreate(int rank, int world, size_t frameBytes, void* handle64, std::string& err);
+int              peerOpen(PeerState* ps, const void* handles, std::string& err);  // world x 64 bytes, in band order
+void             peerClose(PeerState* ps);                                         // unmaps the other bands' buffers
+void             peerDestroy(PeerState* ps);
+uint32_t*        peerFrame(PeerState* ps);
+const PeerTable* peerTable(PeerState* ps);
+int              peerSignal(PeerState* ps, int phase, cudaStream_t s);
+int              peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s);
+int peerScatterRows(PeerState* ps, const uint32_t* fin, int W, int localRows, int stripRows, cudaStream_t s);
 
 int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s);

@@ -20,6 +20,15 @@
 //            guarantees for the tail blend and what the ordered interlock asks for.
 // A tile is owned by one CTA for the whole pass, so its A-buffer slice, aux words and colour samples stay in one SM's
 // L1 and in L2.
+//
+// Fused frame (oit_render, p.fused): the same CTA then composites and resolves its tile (oit_fused.cuh).  The tile's colour
+// samples live in dynamic shared memory for the whole pass (WBOIT: its RGBA16F / R16F targets instead), and for Loop64 /
+// Spinlock (p.onChip) the tile's k-buffer slice + aux words do too, addressed with the reference's own index arithmetic
+// (viewSize = 256).  Only the resolved BGRA8 pixels -- and, for the linked list, the nodes -- ever reach HBM.
+//
+// Tuning record (B200, 4K 8x MSAA linked list; profiles/README.md): 256 threads x 5 CTAs / SM (48 registers) beats 4 x 64
+// registers and 128-thread CTAs; 4 items per thread beats 2 and 8; __match_any_sync bucketing beats ballots; per-pixel
+// sequence counters with spin-waits instead of the per-layer barriers were slower (two block fences per fragment).
 #include "oit_fragment.cuh"
 #include "oit_fused.cuh"
 
@@ -233,6 +242,9 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
 }
 
 // five 256-thread CTAs per SM (<= 51 registers): measured best on B200 (4 CTAs / 64 registers: +6 %, 6 CTAs spill)
+#ifndef OIT_TILE_ORDER
+#define OIT_TILE_ORDER 1
+#endif
 #ifndef OIT_MIN_BLOCKS
 #define OIT_MIN_BLOCKS 5
 #endif
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   __shared__ uint32_t   scanSm[33];
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = OIT_TILE_ORDER ? p.tileOrder[blockIdx.x] : blockIdx.x;  // launch order: longest lists first
   const uint32_t listBegin = p.tileStart[tile], listEnd = p.tileStart[tile + 1];
   const bool     fused = PASS != PASS_OPAQUE && PASS != PASS_LOOP_DEPTH && p.fused != 0;
   if(listBegin == listEnd && !fused)
