@@ -6,7 +6,8 @@
 A step = one frame of the hot path (vertex stage + binning, clears, colour pass(es), composite, resolve [, band gather]).
 `value` is measured with the scene resident in HBM; `e2e` is the same frame through the C ABI with HOST buffers
 (scene + UBO uploaded from pinned memory and the resolved frame read back, every step).  N>1 is sort-first split frame:
-every rank renders its interleaved row strips and ONE NCCL all-gather exchanges the resolved strips.
+every rank renders its interleaved row strips and the frame kernel stores the resolved pixels into every rank's frame
+buffer over NVLink peer memory (fallback / --nccl-gather: ONE ncclAllGather at the end of the frame graph).
 """
 import argparse
 import json
@@ -251,7 +252,8 @@ def run_ours(args):
     peak, peak_src = peaks()
     bytes_stage = algorithmic_bytes(oit, st, {"fragments": F_local, "fragmentsStored": last["fragmentsStored"], "fragmentsTail": last["fragmentsTail"]},
                                     W, s.localRows, verts.shape[0], idx.size)
-    fused = stage_ms["composite"] < 1e-4 and stage_ms["resolve"] < 1e-4
+    # oit_render's fast path (what the library decides in oit_render): one fused kernel whenever something transparent is drawn
+    fused = os.environ.get("OIT_B200_NO_FUSE") is None and st.percentTransparent > 0 and st.numObjects > 0
     if fused:
         # oit_render's fused frame kernel: colour pass + composite + resolve of a tile in one launch; the colour samples
         # stay in shared memory, so the algorithmic bytes of the three reference stages are charged to this one kernel

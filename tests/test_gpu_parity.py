@@ -282,6 +282,16 @@ def test_error_paths(oit_mod):
     assert e.value.code == -3  # OIT_ERR_NO_SCENE
     with pytest.raises(oit_mod.OitError):
         s.setScene(np.zeros((3, 10), np.float32), np.array([0, 1, 5], np.uint32), 3)  # index out of range
+    with pytest.raises(oit_mod.OitError) as e:   # ... which leaves the context without a scene
+        s.onRender(oit_mod.default_camera(64, 64))
+    assert e.value.code == -3
+    import torch
+    bad = torch.tensor([0, 1, 7], dtype=torch.int32, device="cuda")
+    dv = torch.zeros((3, 10), dtype=torch.float32, device="cuda")
+    with pytest.raises(oit_mod.OitError):
+        s.setSceneDevice(dv.data_ptr(), 3, bad.data_ptr(), 3, 3, keepalive=(dv, bad))   # same check for device-resident scenes
+    s.setScene(np.zeros((3, 10), np.float32), np.array([0, 1, 2], np.uint32), 3)
+    s.onRender(oit_mod.default_camera(64, 64))   # a valid scene afterwards renders
     with pytest.raises(oit_mod.OitError):
         s.upload(oit_mod.BUF_AUX, np.zeros(3, np.uint32))  # size mismatch
     s.close()

@@ -159,12 +159,7 @@ void freeBins(BinBuffers& b)
   cudaFree(b.tileStart);
   cudaFree(b.pairInfo);
   cudaFree(b.scratch);
-  for(int i = 0; i < 2; i++)
-  {
-    cudaFree(b.tileKey[i]);
-    cudaFree(b.tileOrder[i]);
-  }
-  cudaFree(b.tileScratch);
+  cudaFree(b.tileOrder);
   b = BinBuffers{};
 }
 
@@ -183,14 +178,9 @@ int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
     CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
   }
   CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 4 * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 4 * sizeof(uint32_t)));
-  for(int i = 0; i < 2; i++)
-  {
-    CUDA_TRY(c, cudaMalloc(&b.tileKey[i], std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
-    CUDA_TRY(c, cudaMalloc(&b.tileOrder[i], std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
-  }
-  CUDA_TRY(c, cudaMalloc(&b.tileScratch, tileScratchWords(numTiles) * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 2 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 2 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.tileOrder, std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
   CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
   c->graphValid = false;  // the captured frame refers to the old buffers
   return OIT_OK;
@@ -289,7 +279,7 @@ void useBins(OitCtx* c, int which)
 {
   c->fp.pairTri   = c->bins[which].pairVal[c->sortedBuf[which]];
   c->fp.tileStart = c->bins[which].tileStart;
-  c->fp.tileOrder = c->bins[which].tileOrder[0];
+  c->fp.tileOrder = c->bins[which].tileOrder;
 }
 
 int ensureSceneBins(OitCtx* c)
@@ -630,6 +620,30 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
   return ensureSceneBins(c);
 }
 
+// every index must refer to an existing vertex: checked on the device, where the index buffer already is (a host loop over
+// the sample's 3.1 M indices costs more than the frame).  On failure the context is left without a scene.
+static int validateIndices(OitCtx* c, const uint32_t* dIndices, uint32_t nIndices, uint32_t nVerts)
+{
+  unsigned long long* flag = (unsigned long long*)c->stats.p + (NUM_STAT_SLOTS - 1);  // no frame is in flight here
+  CUDA_TRY(c, cudaMemsetAsync(flag, 0, sizeof(*flag), c->stream));
+  launchValidateIndices(dIndices, nIndices, nVerts, flag, c->stream);
+  unsigned long long bad = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&bad, flag, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(!bad)
+    return OIT_OK;
+  if(c->sceneOwned)
+  {
+    devFree(c->verts);
+    devFree(c->indices);
+  }
+  c->verts = c->indices = DevBuf{};
+  c->sceneOwned         = true;
+  c->nVerts = c->nIndices = 0;
+  c->graphValid           = false;
+  return fail(c, OIT_ERR_INVALID_ARG, "index out of range");
+}
+
 int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32_t* indices, uint32_t nIndices, uint32_t indicesPerObject)
 {
   if(!c)
@@ -637,9 +651,6 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
   if(!vertices || !indices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  for(uint32_t i = 0; i < nIndices; i++)
-    if(indices[i] >= nVerts)
-      return fail(c, OIT_ERR_INVALID_ARG, "index out of range");
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if(!c->sceneOwned)
   {
@@ -663,6 +674,9 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->verts.p, vertices, (size_t)nVerts * 40, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaMemcpyAsync(c->indices.p, indices, (size_t)nIndices * 4, cudaMemcpyHostToDevice, c->stream));
+  int r = validateIndices(c, (const uint32_t*)c->indices.p, nIndices, nVerts);
+  if(r != OIT_OK)
+    return r;
   if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != indicesPerObject || !c->tv.p)
     return installScene(c, nVerts, nIndices, indicesPerObject);
   c->fp.verts   = (const float*)c->verts.p;
@@ -688,6 +702,9 @@ int oit_set_scene_device(OitCtx* c, const void* dVertices, uint32_t nVerts, cons
   c->verts.bytes   = (size_t)nVerts * 40;
   c->indices.p     = const_cast<uint32_t*>(dIndices);
   c->indices.bytes = (size_t)nIndices * 4;
+  const int r      = validateIndices(c, dIndices, nIndices, nVerts);
+  if(r != OIT_OK)
+    return r;
   return installScene(c, nVerts, nIndices, indicesPerObject);
 }
 
@@ -854,7 +871,10 @@ static int issueFrame(OitCtx* c)
   if((r = oit_draw_opaque(c)) != OIT_OK)
     return r;
   if(exchange && !c->skipGather)
+  {
     c->launches += peerWait(c->peers, PEER_FLAG_READY, (unsigned long long*)c->stats.p, c->stream);
+    record(c, EV_OPAQUE);  // time spent waiting for the other bands is not the colour pass's
+  }
   c->fp.peers = (exchange && c->fp.fused) ? peerTable(c->peers) : nullptr;  // the fused kernel stores to every band
   r           = oit_draw_transparent(c);
   c->fp.peers = nullptr;

@@ -50,6 +50,21 @@ __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
   }
 }
 
+// scene upload: *bad |= 1 if any index refers to a vertex that does not exist (checked where the data already is)
+__global__ void __launch_bounds__(256) k_validate_indices(const uint32_t* __restrict__ indices, uint32_t n, uint32_t nVerts, unsigned long long* bad)
+{
+  bool any = false;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    any |= indices[i] >= nVerts;
+  if(__syncthreads_or(any) && threadIdx.x == 0)
+    atomicOr(bad, 1ull);
+}
+void launchValidateIndices(const uint32_t* indices, uint32_t n, uint32_t nVerts, unsigned long long* bad, cudaStream_t s)
+{
+  const int grid = (int)min((size_t)148 * 8, ((size_t)n + 255) / 256);
+  k_validate_indices<<<grid, 256, 0, s>>>(indices, n, nVerts, bad);
+}
+
 int launchTransformVertices(const FrameParams& p, cudaStream_t s)
 {
   if(p.nVerts == 0)
@@ -341,49 +356,27 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
   }
 }
 
-// heavy tiles first: key = ~(triangles in the tile's list), so that the ascending sort puts the longest lists at the front
-// of the launch order and the light tiles fill the tail of the grid (longest-processing-time-first scheduling)
-__global__ void __launch_bounds__(256) k_tile_cost(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ nOut)
+// Launch order of the raster CTAs: heaviest tiles first, so that the light tiles fill the tail of the grid
+// (longest-processing-time-first scheduling).  A counting sort on min(list length, 1023) by ONE CTA; the order among
+// tiles of equal weight is arbitrary, which is fine: tiles are independent, the order only affects scheduling.
+constexpr int ORDER_BINS = 1024;
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ order)
 {
-  if(blockIdx.x == 0 && threadIdx.x == 0)
-    *nOut = numTiles;
-  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x)
-  {
-    const uint32_t n = min(tileStart[t + 1] - tileStart[t], 0xFFFFu);
-    keys[t]          = 0xFFFFu - n;
-    vals[t]          = t;
-  }
-}
-
-// tileOrder = tile indices sorted by decreasing list length; returns the kernels launched, *sortedBuf = which buffer
-static int launchTileOrder(const BinBuffers& b, uint32_t numTiles, cudaStream_t s)
-{
-  if(numTiles == 0)
-    return 0;
-  const int blocks = (int)min((numTiles + 255u) / 256u, 148u * 4u);
-  k_tile_cost<<<blocks, 256, 0, s>>>(b.tileStart, numTiles, b.tileKey[0], b.tileOrder[0], b.pairInfo + 2);
-  int            launches = 1;
-  const uint32_t nb       = (numTiles + SORT_TILE - 1) / SORT_TILE;
-  uint32_t*      table    = b.tileScratch;
-  uint32_t*      tscan    = table + (size_t)256 * nb + 1;
-  int            cur      = 0;
-  for(int shift = 0; shift < 16; shift += 8)
-  {
-    k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.tileKey[cur], b.pairInfo + 2, shift, table, nb);
-    launches += 1 + launchScan(table, table, (size_t)256 * nb, tscan, s);
-    k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.tileKey[cur], b.tileOrder[cur], b.tileKey[cur ^ 1], b.tileOrder[cur ^ 1], b.pairInfo + 2, shift,
-                                               table, nb);
-    launches++;
-    cur ^= 1;
-  }
-  return launches;  // two passes: the sorted order is back in tileOrder[0]
-}
-size_t tileScratchWords(size_t numTiles)
-{
-  const size_t nb    = (numTiles + SORT_TILE - 1) / SORT_TILE;
-  const size_t table = 256 * nb + 1;
-  return table + scanBlocks(table) + 2;
+  __shared__ uint32_t bins[ORDER_BINS];
+  __shared__ uint32_t scanSm[33];
+  const int           tid = threadIdx.x;
+  bins[tid]               = 0;
+  __syncthreads();
+  for(uint32_t t = tid; t < numTiles; t += 1024)
+    atomicAdd(&bins[ORDER_BINS - 1 - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1)], 1u);  // bin 0 = heaviest
+  __syncthreads();
+  const uint32_t mine = bins[tid];
+  uint32_t       total;
+  const uint32_t excl = blockExclusiveScan(mine, scanSm, total);
+  bins[tid]           = excl;
+  __syncthreads();
+  for(uint32_t t = tid; t < numTiles; t += 1024)
+    order[atomicAdd(&bins[ORDER_BINS - 1 - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1)], 1u)] = t;
 }
 
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t /*numTiles*/)
@@ -433,7 +426,8 @@ int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint
   k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], b.pairInfo, numTiles, b.tileStart);
   launches++;
   *sortedBuf = cur;
-  launches += launchTileOrder(b, numTiles, s);
+  k_tile_order<<<1, 1024, 0, s>>>(b.tileStart, numTiles, b.tileOrder);
+  launches++;
   return launches;
 }
 

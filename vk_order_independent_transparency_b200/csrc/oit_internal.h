@@ -154,6 +154,7 @@ __host__ __device__ inline int tileRowToGlobal(int r, int stripTileRows, int ban
 
 // ---- launchers (each returns the number of kernels it launched) -------------------------------------------------
 int launchTransformVertices(const FrameParams& p, cudaStream_t s);
+void launchValidateIndices(const uint32_t* indices, uint32_t n, uint32_t nVerts, unsigned long long* bad, cudaStream_t s);
 // bins triangles [firstTri, firstTri+triCount) of the index buffer; cullBack for the opaque draw.
 // d_counts/d_offsets: triCount+1 words; returns pair total through *hTotal (synchronises the stream once).
 struct BinBuffers
@@ -162,10 +163,8 @@ struct BinBuffers
   uint32_t* pairKey[2];  // [pairCapacity]
   uint32_t* pairVal[2];
   uint32_t* tileStart;   // [numLocalTiles + 1]
-  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics), [2] tiles
-  uint32_t* tileKey[2];  // [numLocalTiles] launch order of the tiles: heaviest lists first (tileOrder[0] after launchBin)
-  uint32_t* tileOrder[2];
-  uint32_t* tileScratch;
+  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics)
+  uint32_t* tileOrder;   // [numLocalTiles] launch order of the tiles: heaviest lists first
   uint32_t* scratch;     // scan / histogram scratch
   size_t    scratchWords;
   size_t    pairCapacity;
@@ -174,7 +173,6 @@ struct BinBuffers
 int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
               cudaStream_t s);
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
-size_t tileScratchWords(size_t numTiles);
 
 // band gather of the split-frame mode (oit_gather.cu); NCCL is loaded lazily with dlopen
 struct BandGatherState;
