@@ -166,6 +166,23 @@ int oit_generate_scene(const OitConfig* cfg, void* vertices, uint32_t* indices);
 int oit_default_camera(uint32_t width, uint32_t height, float fovDeg, const float eye[3], const float center[3],
                        const float up[3], float zNear, float zFar, OitSceneData* out);
 
+/* ---- instanced scene input: the sphere cloud as a 32-byte-per-object table instead of the flattened mesh.
+   initScene (main.cpp:346-391) draws centre, radius and colour per object and flattens numObjects copies of one UV sphere
+   on the host; here the host hands over only the table and the flattening runs on the device (k_expand_spheres), with the
+   same arithmetic (pos = unit * radius + centre, separate multiply and add), so the vertex / index buffers -- and every
+   result -- are bit-identical to oit_generate_scene + oit_set_scene.  34.8 MB of upload become 32 KB for the default
+   scene. */
+typedef struct OitSphere
+{
+  float center[3];
+  float radius;
+  float color[4]; /* rgb already squared (main.cpp:366-369), alpha */
+} OitSphere;
+/* the table oit_generate_scene flattens: cfg->numObjects entries (numObjects, scaleMin, scaleWidth are read) */
+int oit_generate_spheres(const OitConfig* cfg, OitSphere* spheres);
+/* host pointer, copied; subdiv as in State (2..1024); nSpheres * vertices per sphere must fit 32 bits */
+int oit_set_scene_spheres(OitCtx* ctx, const OitSphere* spheres, uint32_t nSpheres, int32_t subdiv);
+
 /* ---- frame -------------------------------------------------------------------------------------------- */
 /* Sample::onRender (oitRender.cpp:28-154): clear, opaque, transparent colour pass(es), composite, resolve.
    Synchronous: returns when the frame is complete on the device. */

@@ -99,6 +99,13 @@ public:
   {
     check(oit_set_scene(m_ctx, vertices, nVerts, indices, nIndices, indicesPerObject));
   }
+  // the same scene from its 32-byte-per-object table; the mesh is flattened on the device
+  void initSceneInstanced()
+  {
+    std::vector<OitSphere> table((size_t)m_cfg.numObjects);
+    check(oit_generate_spheres(&m_cfg, table.data()));
+    check(oit_set_scene_spheres(m_ctx, table.data(), (uint32_t)table.size(), m_cfg.subdiv));
+  }
 
   void onRender(const OitSceneData& ubo) { check(oit_render(m_ctx, &ubo)); }  // oitRender.cpp:28-154
   void updateUniformBuffer(const OitSceneData& ubo) { check(oit_set_scene_data(m_ctx, &ubo)); }

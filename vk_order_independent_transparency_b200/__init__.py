@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "oit_draw_transparent", "oit_composite", "oit_resolve", "oit_synchronize", "oit_buffer_size", "oit_download",
     "oit_upload", "oit_device_ptr", "oit_read_color", "oit_get_stats", "oit_stream", "oit_local_row_to_global",
     "oit_band_gather_unique_id", "oit_enable_band_gather", "oit_band_peer_export", "oit_band_peer_enable",
-    "oit_band_peer_disable",
+    "oit_band_peer_disable", "oit_generate_spheres", "oit_set_scene_spheres",
 ]
 BUF_FRAME = 10
 
@@ -118,6 +118,8 @@ def load_library():
     L.oit_band_peer_export.argtypes = [vp, vp]
     L.oit_band_peer_enable.argtypes = [vp, vp, C.c_uint32]
     L.oit_band_peer_disable.argtypes = [vp]
+    L.oit_generate_spheres.argtypes = [C.POINTER(OitConfig), vp]
+    L.oit_set_scene_spheres.argtypes = [vp, vp, C.c_uint32, C.c_int32]
     _lib = L
     return L
 
@@ -174,6 +176,17 @@ def generate_scene(state):
     idx = np.empty(ni.value, np.uint32)
     L.oit_generate_scene(C.byref(cfg), verts.ctypes.data, idx.ctypes.data)
     return verts, idx, ipo.value
+
+
+def generate_spheres(state):
+    """The per-object table initScene draws (main.cpp:350-369): float32 [numObjects, 8] = centre xyz, radius, colour rgba
+    (32 bytes per object instead of the flattened mesh; Sample.setSceneSpheres flattens it on the device)."""
+    L = load_library()
+    cfg = state.to_config(16, 16)
+    table = np.empty((max(int(state.numObjects), 0), 8), np.float32)
+    if L.oit_generate_spheres(C.byref(cfg), table.ctypes.data) != 0:
+        raise OitError(-1, "bad scene parameters")
+    return table
 
 
 def default_camera(width, height, fov=45.0, eye=(0.0, 0.0, 12.0), center=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), near=0.1, far=100.0):
@@ -255,6 +268,12 @@ class Sample:
         verts = np.ascontiguousarray(verts, np.float32)
         idx = np.ascontiguousarray(idx, np.uint32)
         self._check(self.L.oit_set_scene(self.h, verts.ctypes.data, verts.shape[0], idx.ctypes.data, idx.size, indicesPerObject))
+
+    def setSceneSpheres(self, table, subdiv=None):
+        """Instanced scene input: `table` float32 [n, 8] (generate_spheres); the mesh is flattened on the device."""
+        table = np.ascontiguousarray(table, np.float32).reshape(-1, 8)
+        self._check(self.L.oit_set_scene_spheres(self.h, table.ctypes.data, table.shape[0],
+                                                 int(self.state.subdiv if subdiv is None else subdiv)))
 
     def setSceneDevice(self, dverts_ptr, nVerts, didx_ptr, nIndices, indicesPerObject, keepalive=None):
         self._scene_keepalive = keepalive

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "oit_internal.h"
+#include "oit_scene.h"
 
 using namespace oit;
 
@@ -100,6 +101,9 @@ struct OitCtx
   bool             skipGather = false;  // re-render after a buffer growth: the frame's one collective already ran
   bool             finOwned   = true;   // false once `fin` is this rank's slice of the gather buffer
   // split frame over peer memory (oit_peer.cu): the frame kernel stores into every band's frame buffer
+  // instanced scene input (oit_set_scene_spheres): the object table and the unit-sphere template of `sphSubdiv`
+  DevBuf sphTable, sphUnitPos, sphUnitTri;
+  int    sphSubdiv = 0;
   PeerState* peers     = nullptr;
   bool       peersOpen = false;
   uint64_t        graphLaunches = 0;
@@ -550,7 +554,7 @@ int oit_destroy(OitCtx* c)
   if(!c->finOwned)
     c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
-                   &c->tables, &c->stats, &c->tv, &c->gatherBuf, &c->frame})
+                   &c->tables, &c->stats, &c->tv, &c->gatherBuf, &c->frame, &c->sphTable, &c->sphUnitPos, &c->sphUnitTri})
     devFree(*b);
   if(c->sceneOwned)
   {
@@ -706,6 +710,62 @@ int oit_set_scene_device(OitCtx* c, const void* dVertices, uint32_t nVerts, cons
   if(r != OIT_OK)
     return r;
   return installScene(c, nVerts, nIndices, indicesPerObject);
+}
+
+int oit_set_scene_spheres(OitCtx* c, const OitSphere* spheres, uint32_t nSpheres, int32_t subdiv)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  OitConfig sizes   = c->cfg;
+  sizes.numObjects  = (int32_t)nSpheres;
+  sizes.subdiv      = subdiv;
+  uint32_t nVerts = 0, nIndices = 0, ipo = 0;
+  if(!spheres || nSpheres == 0 || nSpheres > 0x7FFFFFFFu || oit_scene_sizes(&sizes, &nVerts, &nIndices, &ipo) != OIT_OK)
+    return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  int r;
+  if(c->sphSubdiv != subdiv)
+  {
+    std::vector<float>    pos;
+    std::vector<uint32_t> tri;
+    unitSphereTemplate(subdiv, pos, tri);
+    if((r = devAlloc(c, c->sphUnitPos, pos.size() * sizeof(float))) != OIT_OK || (r = devAlloc(c, c->sphUnitTri, tri.size() * sizeof(uint32_t))) != OIT_OK)
+      return r;
+    CUDA_TRY(c, cudaMemcpy(c->sphUnitPos.p, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->sphUnitTri.p, tri.data(), tri.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->sphSubdiv = subdiv;
+  }
+  if(c->sphTable.bytes != (size_t)nSpheres * sizeof(OitSphere) && (r = devAlloc(c, c->sphTable, (size_t)nSpheres * sizeof(OitSphere))) != OIT_OK)
+    return r;
+  if(!c->sceneOwned)
+  {
+    c->verts   = DevBuf{};
+    c->indices = DevBuf{};
+  }
+  c->sceneOwned = true;
+  if(c->verts.bytes != (size_t)nVerts * 40)
+  {
+    c->graphValid = false;
+    if((r = devAlloc(c, c->verts, (size_t)nVerts * 40)) != OIT_OK)
+      return r;
+  }
+  if(c->indices.bytes != (size_t)nIndices * 4)
+  {
+    c->graphValid = false;
+    if((r = devAlloc(c, c->indices, (size_t)nIndices * 4)) != OIT_OK)
+      return r;
+  }
+  // the only upload: 32 bytes per object; the flattening runs where the mesh is needed
+  CUDA_TRY(c, cudaMemcpyAsync(c->sphTable.p, spheres, (size_t)nSpheres * sizeof(OitSphere), cudaMemcpyHostToDevice, c->stream));
+  launchExpandSpheres((const float*)c->sphTable.p, nSpheres, (const float*)c->sphUnitPos.p, nVerts / nSpheres, (const uint32_t*)c->sphUnitTri.p,
+                      ipo, (float*)c->verts.p, (uint32_t*)c->indices.p, c->stream);
+  CUDA_TRY(c, cudaGetLastError());
+  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != ipo || !c->tv.p)
+    return installScene(c, nVerts, nIndices, ipo);
+  c->fp.verts   = (const float*)c->verts.p;
+  c->fp.indices = (const uint32_t*)c->indices.p;
+  return OIT_OK;
 }
 
 int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)

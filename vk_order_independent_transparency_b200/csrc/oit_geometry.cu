@@ -65,6 +65,44 @@ void launchValidateIndices(const uint32_t* indices, uint32_t n, uint32_t nVerts,
   k_validate_indices<<<grid, 256, 0, s>>>(indices, n, nVerts, bad);
 }
 
+// instanced scene input: flattens numObjects copies of the unit sphere on the device, with the arithmetic of
+// the host generator (oit_scene.cpp: pos = unit * radius + centre as a separate multiply and add), 40-byte vertices
+__global__ void __launch_bounds__(256) k_expand_spheres(const float* __restrict__ spheres, uint32_t nSpheres, const float* __restrict__ unitPos,
+                                                        uint32_t vPer, const uint32_t* __restrict__ unitTri, uint32_t iPer,
+                                                        float* __restrict__ verts, uint32_t* __restrict__ indices)
+{
+  const size_t nV = (size_t)nSpheres * vPer, nI = (size_t)nSpheres * iPer;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nV + nI; i += (size_t)gridDim.x * blockDim.x)
+  {
+    if(i < nV)
+    {
+      const uint32_t obj = (uint32_t)(i / vPer), v = (uint32_t)(i - (size_t)obj * vPer);
+      const float4   a = __ldg(reinterpret_cast<const float4*>(spheres) + 2 * (size_t)obj);      // centre, radius
+      const float4   c = __ldg(reinterpret_cast<const float4*>(spheres) + 2 * (size_t)obj + 1);  // colour
+      const float    px = unitPos[3 * v], py = unitPos[3 * v + 1], pz = unitPos[3 * v + 2];
+      float2*        d  = reinterpret_cast<float2*>(verts + i * 10);  // 40-byte stride: 8-byte aligned
+      d[0]              = make_float2(__fadd_rn(__fmul_rn(px, a.w), a.x), __fadd_rn(__fmul_rn(py, a.w), a.y));
+      d[1]              = make_float2(__fadd_rn(__fmul_rn(pz, a.w), a.z), px);
+      d[2]              = make_float2(py, pz);
+      d[3]              = make_float2(c.x, c.y);
+      d[4]              = make_float2(c.z, c.w);
+    }
+    else
+    {
+      const size_t   j   = i - nV;
+      const uint32_t obj = (uint32_t)(j / iPer), k = (uint32_t)(j - (size_t)obj * iPer);
+      indices[j]         = obj * vPer + unitTri[k];
+    }
+  }
+}
+void launchExpandSpheres(const float* spheres, uint32_t nSpheres, const float* unitPos, uint32_t vPer, const uint32_t* unitTri, uint32_t iPer,
+                         float* verts, uint32_t* indices, cudaStream_t s)
+{
+  const size_t total = (size_t)nSpheres * vPer + (size_t)nSpheres * iPer;
+  const int    grid  = (int)min((size_t)148 * 16, (total + 255) / 256);
+  k_expand_spheres<<<grid, 256, 0, s>>>(spheres, nSpheres, unitPos, vPer, unitTri, iPer, verts, indices);
+}
+
 int launchTransformVertices(const FrameParams& p, cudaStream_t s)
 {
   if(p.nVerts == 0)

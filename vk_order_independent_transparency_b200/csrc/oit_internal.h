@@ -154,6 +154,8 @@ __host__ __device__ inline int tileRowToGlobal(int r, int stripTileRows, int ban
 
 // ---- launchers (each returns the number of kernels it launched) -------------------------------------------------
 int launchTransformVertices(const FrameParams& p, cudaStream_t s);
+void launchExpandSpheres(const float* spheres, uint32_t nSpheres, const float* unitPos, uint32_t vPer, const uint32_t* unitTri, uint32_t iPer,
+                         float* verts, uint32_t* indices, cudaStream_t s);
 void launchValidateIndices(const uint32_t* indices, uint32_t n, uint32_t nVerts, unsigned long long* bad, cudaStream_t s);
 // bins triangles [firstTri, firstTri+triCount) of the index buffer; cullBack for the opaque draw.
 // d_counts/d_offsets: triCount+1 words; returns pair total through *hTotal (synchronises the stream once).

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/oit_b200.h"
+#include "oit_scene.h"
 
 namespace {
 
@@ -83,47 +84,60 @@ int oit_scene_sizes(const OitConfig* cfg, uint32_t* nVerts, uint32_t* nIndices, 
   return OIT_OK;
 }
 
+int oit_generate_spheres(const OitConfig* cfg, OitSphere* spheres)
+{
+  if(!spheres || oit_scene_sizes(cfg, nullptr, nullptr, nullptr) != OIT_OK)
+    return OIT_ERR_INVALID_ARG;
+  MinStd      rng{3625};                          // main.cpp:350
+  const float kGlobalScale = 8.0f, kGrid = 16.0f;  // GLOBAL_SCALE, GRID_SIZE (main.cpp:54-55)
+  for(int obj = 0; obj < cfg->numObjects; obj++)
+  {
+    OitSphere& o = spheres[obj];
+    // glm::vec3 center(u(), u(), u()): z is drawn first, x last
+    o.center[2] = rng.next();
+    o.center[1] = rng.next();
+    o.center[0] = rng.next();
+    for(float& v : o.center)
+      v = (v - 0.5f) * kGlobalScale;
+    float radius = kGlobalScale * 0.9f / kGrid;
+    radius *= rng.next() * cfg->scaleWidth + cfg->scaleMin;
+    o.radius = radius;
+    // glm::vec4 color(u(), u(), u(), u()): alpha first, red last; rgb squared (main.cpp:366-369)
+    o.color[3] = rng.next();
+    o.color[2] = rng.next();
+    o.color[1] = rng.next();
+    o.color[0] = rng.next();
+    o.color[0] *= o.color[0];
+    o.color[1] *= o.color[1];
+    o.color[2] *= o.color[2];
+  }
+  return OIT_OK;
+}
+
 int oit_generate_scene(const OitConfig* cfg, void* vertices, uint32_t* indices)
 {
   uint32_t nv, ni, ipo;
   if(!vertices || !indices || oit_scene_sizes(cfg, &nv, &ni, &ipo) != OIT_OK)
     return OIT_ERR_INVALID_ARG;
-  const UnitSphere sphere = makeUnitSphere(cfg->subdiv);
-  const uint32_t   vPer   = (uint32_t)(sphere.pos.size() / 3);
-  float*           out    = static_cast<float*>(vertices);
-  MinStd           rng{3625};                          // main.cpp:350
-  const float      kGlobalScale = 8.0f, kGrid = 16.0f;  // GLOBAL_SCALE, GRID_SIZE (main.cpp:54-55)
+  const UnitSphere       sphere = makeUnitSphere(cfg->subdiv);
+  const uint32_t         vPer   = (uint32_t)(sphere.pos.size() / 3);
+  float*                 out    = static_cast<float*>(vertices);
+  std::vector<OitSphere> table((size_t)cfg->numObjects);
+  oit_generate_spheres(cfg, table.data());
   for(int obj = 0; obj < cfg->numObjects; obj++)
   {
-    // glm::vec3 center(u(), u(), u()): z is drawn first, x last
-    float c[3];
-    c[2] = rng.next();
-    c[1] = rng.next();
-    c[0] = rng.next();
-    for(float& v : c)
-      v = (v - 0.5f) * kGlobalScale;
-    float radius = kGlobalScale * 0.9f / kGrid;
-    radius *= rng.next() * cfg->scaleWidth + cfg->scaleMin;
-    // glm::vec4 color(u(), u(), u(), u()): alpha first, red last; rgb squared (main.cpp:366-369)
-    float col[4];
-    col[3] = rng.next();
-    col[2] = rng.next();
-    col[1] = rng.next();
-    col[0] = rng.next();
-    col[0] *= col[0];
-    col[1] *= col[1];
-    col[2] *= col[2];
-    float* dst = out + (size_t)obj * vPer * 10;
+    const OitSphere& o   = table[(size_t)obj];
+    float*           dst = out + (size_t)obj * vPer * 10;
     for(uint32_t v = 0; v < vPer; v++, dst += 10)
     {
       const float* p = &sphere.pos[(size_t)v * 3];
-      dst[0]         = p[0] * radius + c[0];
-      dst[1]         = p[1] * radius + c[1];
-      dst[2]         = p[2] * radius + c[2];
+      dst[0]         = p[0] * o.radius + o.center[0];
+      dst[1]         = p[1] * o.radius + o.center[1];
+      dst[2]         = p[2] * o.radius + o.center[2];
       dst[3]         = p[0];
       dst[4]         = p[1];
       dst[5]         = p[2];
-      memcpy(dst + 6, col, sizeof(col));
+      memcpy(dst + 6, o.color, sizeof(o.color));
     }
     uint32_t* idst = indices + (size_t)obj * ipo;
     for(uint32_t i = 0; i < ipo; i++)
@@ -197,3 +211,12 @@ int oit_default_camera(uint32_t width, uint32_t height, float fovDeg, const floa
 }
 
 }  // extern "C"
+
+namespace oit {
+void unitSphereTemplate(int subdiv, std::vector<float>& pos, std::vector<uint32_t>& tri)
+{
+  UnitSphere m = makeUnitSphere(subdiv);
+  pos.swap(m.pos);
+  tri.swap(m.tri);
+}
+}  // namespace oit
