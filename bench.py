@@ -180,7 +180,7 @@ def run_ours(args):
             band_gather.gather(fin_dev)
 
     def step_resident():
-        s.onRender(ubo)                      # render (+ in-library band gather): complete on the device when this returns
+        s.onRender(ubo)                      # render (+ in-library band exchange): enqueued on the library's stream; up to 4 frames in flight
         if band_gather is not None:
             gather()
 
@@ -194,6 +194,7 @@ def run_ours(args):
     def timed(step, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
             step()
+        s.synchronize()   # oit_render is asynchronous: completes the warm-up frames (and their one-off buffer growth)
         barrier()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:

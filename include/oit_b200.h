@@ -185,7 +185,12 @@ int oit_set_scene_spheres(OitCtx* ctx, const OitSphere* spheres, uint32_t nSpher
 
 /* ---- frame -------------------------------------------------------------------------------------------- */
 /* Sample::onRender (oitRender.cpp:28-154): clear, opaque, transparent colour pass(es), composite, resolve.
-   Synchronous: returns when the frame is complete on the device. */
+   Asynchronous, like recording + submitting the frame's command buffer: the frame is enqueued on the context's stream
+   (one CUDA graph launch) and may still be running when the call returns; up to 4 frames can be in flight.  A frame is
+   COMPLETED -- waited for, and rendered again if one of the library's internal buffers had to grow -- by oit_synchronize,
+   oit_download / oit_read_color, oit_get_stats, by every scene change and by the stage-by-stage calls below.  Hosts that
+   consume oit_device_ptr() memory directly call oit_synchronize first.  OIT_B200_SYNC_RENDER=1 in the environment makes
+   oit_render complete its frame before returning. */
 int oit_render(OitCtx* ctx, const OitSceneData* ubo);
 /* the same stage by stage, for tests and for hosts that interleave their own work (each is asynchronous on the
    context's stream; oit_synchronize waits) */
@@ -224,7 +229,7 @@ int oit_enable_band_gather(OitCtx* ctx, const void* id128);
    oit_band_peer_enable, which maps the other bands' buffers.  From then on the frame kernel of oit_render stores every
    resolved pixel straight into ALL bands' frame buffers while it renders (no collective after the frame), and two flag
    rounds per frame (device-side sequence numbers, part of the frame graph) keep the bands in step; OIT_BUF_FRAME holds
-   the whole frame on every band when oit_render returns.  Every band must call oit_render the same number of times.
+   the whole frame on every band once the frame is complete (oit_synchronize).  Every band must call oit_render the same number of times.
    Tear-down: all bands finish rendering, host barrier, oit_band_peer_disable on every band, host barrier, oit_destroy.
    Returns OIT_ERR_UNSUPPORTED when the devices cannot map each other's memory (fall back to the NCCL gather above). */
 int oit_band_peer_export(OitCtx* ctx, void* handle64);

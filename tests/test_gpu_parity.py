@@ -263,16 +263,47 @@ def test_reuse_and_idempotence(oit_mod, oracle_mod):
     s.close()
 
 
-@pytest.mark.parametrize("mode", ["onchip_all", "no_onchip", "no_fuse", "no_graph"])
+@pytest.mark.parametrize("mode", ["onchip_all", "no_onchip", "no_fuse", "no_graph", "sync_render"])
 @pytest.mark.parametrize("alg,aa,L", [(0, 0, 8), (0, 1, 4), (3, 0, 8), (3, 4, 2), (4, 1, 8), (5, 0, 8), (5, 4, 4), (6, 4, 8), (1, 1, 8)])
 def test_frame_path_variants(oit_mod, oracle_mod, monkeypatch, mode, alg, aa, L):
     """Every way oit_render can execute a frame gives the oracle's image: k-buffer slice in shared memory for all
     techniques that support it, in HBM for all, staged (unfused) kernels, and plain stream launches instead of the graph."""
     monkeypatch.setenv({"onchip_all": "OIT_B200_ONCHIP_ALL", "no_onchip": "OIT_B200_NO_ONCHIP", "no_fuse": "OIT_B200_NO_FUSE",
-                        "no_graph": "OIT_B200_NO_GRAPH"}[mode], "1")
+                        "no_graph": "OIT_B200_NO_GRAPH", "sync_render": "OIT_B200_SYNC_RENDER"}[mode], "1")
     s, o = run_pair(oit_mod, oracle_mod, 176, 120, algorithm=alg, aaType=aa, oitLayers=L, numObjects=180, subdiv=7)
     assert_frames_equal(s, o)
     s.close()
+
+
+@pytest.mark.parametrize("alg,aa", [(1, 4), (3, 0), (6, 1)])
+def test_frames_in_flight(oit_mod, alg, aa):
+    """oit_render only enqueues: several frames with different cameras back to back (more than the UBO staging ring holds,
+    starting on a fresh context whose pair buffers still have to grow), and what is read afterwards is the LAST camera's
+    frame -- the same as rendering just that camera on its own context."""
+    st = oit_mod.State(algorithm=alg, aaType=aa, numObjects=300, subdiv=8, linkedListAllocatedPerElement=40)
+    W, H = 256, 160
+    cams = [oit_mod.default_camera(W, H, eye=(0.3 * i, -0.2 * i, 12.0 - 0.5 * i)) for i in range(9)]
+    s = oit_mod.Sample(st, W, H)
+    s.initScene()
+    for cam in cams:
+        s.onRender(cam)
+    got, got_stats = s.readColor(), s.stats()
+    r = oit_mod.Sample(st, W, H)
+    r.initScene()
+    r.onRender(cams[-1])
+    r.synchronize()
+    assert np.array_equal(got, r.readColor())
+    assert got_stats["fragments"] == r.stats()["fragments"]
+    # the stage-by-stage entry points complete a frame that is still in flight before they start
+    s.onRender(cams[0])
+    s.updateUniformBuffer(cams[-1])
+    s.beginFrame()
+    s.drawOpaque()
+    getattr(s, "drawTransparent" + {1: "LinkedList", 3: "Loop64", 6: "Weighted"}[alg])()
+    s.copyOffscreenToBackBuffer()
+    assert np.array_equal(s.readColor(), got)
+    s.close()
+    r.close()
 
 
 def test_error_paths(oit_mod):

@@ -59,10 +59,12 @@ for mode in modes:
     if (s.enableBandPeers(dist) if mode == "peers" else (s.enableBandGather(dist), True)[1]):
         for _ in range(5):
             s.onRender(ubo)
+        s.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(20):
             s.onRender(ubo)
+        s.synchronize()   # oit_render only enqueues
         ms = torch.tensor([(time.perf_counter() - t0) / 20 * 1e3], device="cuda")
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         if rank == 0:

@@ -58,6 +58,8 @@ enum EventId
 };
 }  // namespace
 
+constexpr int UBO_RING = 4;
+
 struct OitCtx
 {
   OitConfig    cfg{};
@@ -84,7 +86,11 @@ struct OitCtx
   uint32_t   drawTris[2]{};
   // per-frame UBO in device memory + its pinned staging copy; the captured frame graph
   DevBuf          uboDev;
-  DeviceUbo*      hostUbo    = nullptr;
+  DeviceUbo*      hostUbo    = nullptr;  // pinned staging ring of UBO_RING entries (frames may be in flight)
+  cudaEvent_t     uboEv[UBO_RING]{};     // recorded after the upload out of slot i
+  int             uboSlot      = 0;
+  bool            framePending = false;  // oit_render enqueued a frame whose overflow check has not run yet
+  bool            asyncRender  = true;   // oit_render returns once the frame is enqueued (OIT_B200_SYNC_RENDER=1: waits)
   cudaGraph_t     graph      = nullptr;
   cudaGraphExec_t graphExec  = nullptr;
   bool            graphValid = false;
@@ -312,6 +318,8 @@ int ensureSceneBins(OitCtx* c)
 // ====================================================================================================================
 extern "C" {
 
+static int finishFrame(OitCtx* c);
+
 int oit_abi_version(void) { return OIT_B200_ABI_VERSION; }
 
 void oit_default_config(OitConfig* cfg)
@@ -417,10 +425,13 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   for(int i = 0; i < NUM_EVENTS; i++)
     CREATE_CUDA(cudaEventCreate(&c->ev[i]));
   CREATE_CUDA(cudaMallocHost(&c->hostScalar, 64));
-  CREATE_CUDA(cudaMallocHost(&c->hostUbo, sizeof(DeviceUbo)));
+  CREATE_CUDA(cudaMallocHost(&c->hostUbo, UBO_RING * sizeof(DeviceUbo)));
+  for(int i = 0; i < UBO_RING; i++)
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->uboEv[i], cudaEventDisableTiming));
+  c->asyncRender = getenv("OIT_B200_SYNC_RENDER") == nullptr;
   CREATE_CUDA(cudaMallocHost(&c->hostMirror, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long)));
   memset(c->hostMirror, 0, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long));
-  memset(c->hostUbo, 0, sizeof(DeviceUbo));
+  memset(c->hostUbo, 0, UBO_RING * sizeof(DeviceUbo));
   c->useGraph = getenv("OIT_B200_NO_GRAPH") == nullptr;
 
   // tile / band geometry
@@ -570,6 +581,9 @@ int oit_destroy(OitCtx* c)
     cudaFreeHost(c->hostScalar);
   if(c->hostUbo)
     cudaFreeHost(c->hostUbo);
+  for(int i = 0; i < UBO_RING; i++)
+    if(c->uboEv[i])
+      cudaEventDestroy(c->uboEv[i]);
   if(c->hostMirror)
     cudaFreeHost(c->hostMirror);
   if(c->graphExec)
@@ -655,7 +669,8 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
   if(!vertices || !indices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   if(!c->sceneOwned)
   {
     c->verts   = DevBuf{};
@@ -695,7 +710,8 @@ int oit_set_scene_device(OitCtx* c, const void* dVertices, uint32_t nVerts, cons
   if(!dVertices || !dIndices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   if(c->sceneOwned)
   {
     devFree(c->verts);
@@ -723,7 +739,8 @@ int oit_set_scene_spheres(OitCtx* c, const OitSphere* spheres, uint32_t nSpheres
   if(!spheres || nSpheres == 0 || nSpheres > 0x7FFFFFFFu || oit_scene_sizes(&sizes, &nVerts, &nIndices, &ipo) != OIT_OK)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   int r;
   if(c->sphSubdiv != subdiv)
   {
@@ -779,14 +796,18 @@ int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
   c->ubo.viewport[2] = (int32_t)(c->bufW * c->bufH);
   c->ubo.linkedListAllocatedPerElement =
       c->cfg.algorithm == OIT_LINKEDLIST ? c->fp.capacity : c->cfg.oitLayers * (uint32_t)c->fp.layers;
-  // the previous frame may still be reading the staging copy
+  // frames may be in flight: the upload goes through a ring of pinned staging slots; waiting for a slot's previous upload
+  // also bounds the number of frames the host can run ahead of the device
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  memcpy(c->hostUbo->projView, ubo->projViewMatrix, sizeof(float) * 16);
-  memcpy(c->hostUbo->view, ubo->viewMatrix, sizeof(float) * 16);
-  c->hostUbo->alphaMin   = ubo->alphaMin;
-  c->hostUbo->alphaWidth = ubo->alphaWidth;
-  CUDA_TRY(c, cudaMemcpyAsync(c->uboDev.p, c->hostUbo, sizeof(DeviceUbo), cudaMemcpyHostToDevice, c->stream));
+  c->uboSlot      = (c->uboSlot + 1) % UBO_RING;
+  DeviceUbo* slot = c->hostUbo + c->uboSlot;
+  CUDA_TRY(c, cudaEventSynchronize(c->uboEv[c->uboSlot]));
+  memcpy(slot->projView, ubo->projViewMatrix, sizeof(float) * 16);
+  memcpy(slot->view, ubo->viewMatrix, sizeof(float) * 16);
+  slot->alphaMin   = ubo->alphaMin;
+  slot->alphaWidth = ubo->alphaWidth;
+  CUDA_TRY(c, cudaMemcpyAsync(c->uboDev.p, slot, sizeof(DeviceUbo), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(c, cudaEventRecord(c->uboEv[c->uboSlot], c->stream));
   c->haveUbo       = true;
   return OIT_OK;
 }
@@ -800,6 +821,9 @@ int oit_begin_frame(OitCtx* c)
   if(!c->haveUbo)
     return fail(c, OIT_ERR_INVALID_ARG, "oit_set_scene_data has not been called");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(!c->capturing && c->framePending)
+    if(const int fr = finishFrame(c); fr != OIT_OK)
+      return fr;
   c->launches = 0;
   for(bool& b : c->evRecorded)
     b = false;
@@ -913,7 +937,8 @@ int oit_synchronize(OitCtx* c)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   return OIT_OK;
 }
 
@@ -973,14 +998,11 @@ static int issueFrame(OitCtx* c)
   return OIT_OK;
 }
 
-int oit_render(OitCtx* c, const OitSceneData* ubo)
+// Enqueues one frame on the context's stream (graph replay, or plain launches) without waiting for it.
+static int enqueueFrame(OitCtx* c)
 {
-  int r;
-  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
-    return r;
-  if(!c->verts.p || !c->indices.p)
-    return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
-  for(int attempt = 0; attempt < 4; attempt++)
+  int r = OIT_OK;
+  for(int tries = 0; tries < 2; tries++)
   {
     if((r = ensureSceneBins(c)) != OIT_OK)
       return r;
@@ -1000,6 +1022,7 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
                          ? 1
                          : 0;
     }
+    bool retry = false;
     // (with the band gather, the first frame runs un-captured so that NCCL sets up its connections outside a capture)
     if(c->useGraph && (!c->gather || c->gatherWarm))
     {
@@ -1023,23 +1046,21 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
         if(r != OIT_OK || e != cudaSuccess)
         {
           cudaGetLastError();
-          c->useGraph  = false;  // fall back to plain stream launches
-          c->capturing = false;
-    c->fp.fused  = 0;
-    c->fp.onChip = 0;
-          continue;
+          c->useGraph = false;  // fall back to plain stream launches
+          retry       = true;
         }
-        c->graphValid    = true;
-        c->graphLaunches = c->launches;
+        else
+        {
+          c->graphValid    = true;
+          c->graphLaunches = c->launches;
+        }
       }
-      c->launches = c->graphLaunches;
-      cudaError_t e = cudaGraphLaunch(c->graphExec, c->stream);
-      if(e != cudaSuccess)
+      if(!retry)
       {
-        c->capturing = false;
-    c->fp.fused  = 0;
-    c->fp.onChip = 0;
-        return fail(c, OIT_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+        c->launches         = c->graphLaunches;
+        const cudaError_t e = cudaGraphLaunch(c->graphExec, c->stream);
+        if(e != cudaSuccess)
+          r = fail(c, OIT_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
       }
     }
     else
@@ -1047,14 +1068,31 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     c->capturing = false;
     c->fp.fused  = 0;
     c->fp.onChip = 0;
-    if(r != OIT_OK)
+    if(!retry)
       return r;
-    if((r = oit_synchronize(c)) != OIT_OK)
-      return r;
-    bool grown     = false;
-    c->mirrorValid = true;
-    r              = growBinsIfNeeded(c, &grown);
-    c->mirrorValid = false;
+  }
+  return r;
+}
+
+// Completes the frame oit_render enqueued: waits for it, and if a (tile, triangle) pair buffer overflowed (normally only
+// the first frame after a scene / camera change) grows it and renders the frame again.  Every entry point that hands
+// results to the host, or changes what a frame reads, comes through here; without a pending frame it is a stream sync.
+static int finishFrame(OitCtx* c)
+{
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(!c->framePending)
+  {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return OIT_OK;
+  }
+  for(int attempt = 0; attempt < 4; attempt++)
+  {
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->framePending = false;
+    bool grown      = false;
+    c->mirrorValid  = true;
+    int r           = growBinsIfNeeded(c, &grown);
+    c->mirrorValid  = false;
     if(r != OIT_OK)
       return r;
     if(c->hostMirror[STAT_PEER_TIMEOUT] != 0)
@@ -1064,9 +1102,9 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
       c->gatherWarm = true;
       if(c->skipGather)
       {
-        // this was the re-render after a pair-buffer growth: the collective already ran (once per oit_render on every
-        // rank, or the ranks would deadlock), so the other ranks keep this band's strips of the overflowed attempt for
-        // this one frame.  Only happens on the first frame(s) after a scene / camera change that needs larger buffers.
+        // this was the re-render after a pair-buffer growth: the exchange round already ran (once per oit_render on every
+        // rank, or the ranks would deadlock), so with the NCCL gather the other ranks keep this band's strips of the
+        // overflowed attempt for this one frame (the peer-memory path still stores the re-rendered strips everywhere).
         c->skipGather = false;
         c->graphValid = false;
       }
@@ -1075,8 +1113,36 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     }
     if(!grown)
       return OIT_OK;
+    if((r = enqueueFrame(c)) != OIT_OK)
+      return r;
+    c->framePending = true;
   }
   return fail(c, OIT_ERR_OUT_OF_MEMORY, "the (tile, triangle) pair buffers kept overflowing");
+}
+
+int oit_render(OitCtx* c, const OitSceneData* ubo)
+{
+  if(!c)
+    return OIT_ERR_INVALID_ARG;
+  int r;
+  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
+    return r;
+  if(!c->verts.p || !c->indices.p)
+    return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
+  // a frame in flight that already reported a pair-buffer overflow (the mirror is pinned host memory written by the frame's
+  // last nodes): grow the buffers now instead of letting further frames run with truncated triangle lists
+  if(c->framePending && reinterpret_cast<volatile unsigned long long*>(c->hostMirror)[STAT_OVERFLOW] != 0)
+    if((r = finishFrame(c)) != OIT_OK)
+      return r;
+  if((r = enqueueFrame(c)) != OIT_OK)
+    return r;
+  c->framePending = true;
+  // asynchronous by default: the frame (and the frames before it) may still be running when this returns; oit_synchronize,
+  // oit_download / oit_read_color, oit_get_stats and every scene change complete it first.  The NCCL gather's first,
+  // un-captured frame and OIT_B200_SYNC_RENDER=1 wait here.
+  if(!c->asyncRender || (c->gather && !c->gatherWarm))
+    return finishFrame(c);
+  return OIT_OK;
 }
 
 int oit_get_stats(OitCtx* c, OitStats* out)
@@ -1084,7 +1150,8 @@ int oit_get_stats(OitCtx* c, OitStats* out)
   if(!c || !out)
     return OIT_ERR_INVALID_ARG;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   unsigned long long h[NUM_STAT_SLOTS];
   CUDA_TRY(c, cudaMemcpy(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
   OitStats s{};
@@ -1144,6 +1211,8 @@ int oit_download(OitCtx* c, OitBuffer which, void* host, size_t bytes)
   if(bytes != b->bytes)
     return fail(c, OIT_ERR_SIZE, "host size does not match the device buffer");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   CUDA_TRY(c, cudaMemcpyAsync(host, b->p, bytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return OIT_OK;
@@ -1159,6 +1228,8 @@ int oit_upload(OitCtx* c, OitBuffer which, const void* host, size_t bytes)
   if(bytes != b->bytes)
     return fail(c, OIT_ERR_SIZE, "host size does not match the device buffer");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   CUDA_TRY(c, cudaMemcpyAsync(b->p, host, bytes, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return OIT_OK;
@@ -1198,7 +1269,8 @@ int oit_enable_band_gather(OitCtx* c, const void* id128)
   if(c->cfg.width % 4)
     return fail(c, OIT_ERR_INVALID_ARG, "the band gather needs a width that is a multiple of 4");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   // rows of the largest band: every rank contributes a slice of that many (padded) rows
   uint32_t pad = 0;
   for(uint32_t b = 0; b < c->cfg.bandCount; b++)
@@ -1241,7 +1313,8 @@ int oit_band_peer_export(OitCtx* c, void* handle64)
   if(c->cfg.width % 4)
     return fail(c, OIT_ERR_INVALID_ARG, "the split-frame exchange needs a width that is a multiple of 4");
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   if(c->peers)
     return fail(c, OIT_ERR_INVALID_ARG, "oit_band_peer_export has already been called");
   const size_t bytes = (size_t)c->cfg.width * c->cfg.height * 4;
@@ -1263,7 +1336,8 @@ int oit_band_peer_enable(OitCtx* c, const void* handles, uint32_t count)
   if(c->peersOpen)
     return OIT_OK;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   const int r = peerOpen(c->peers, handles, c->error);
   if(r != OIT_OK)
     return r;
@@ -1280,7 +1354,8 @@ int oit_band_peer_disable(OitCtx* c)
   if(!c->peers)
     return OIT_OK;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
+    return fr;
   c->graphValid = false;
   if(c->peersOpen)
   {
