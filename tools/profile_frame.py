@@ -13,6 +13,9 @@ st = oit.State(**kw)
 s = oit.Sample(st, W, H)
 s.initScene()
 ubo = oit.default_camera(W, H)
+s.onRender(ubo)
+s.synchronize()   # the first frame sizes the pair buffers (and is rendered again): keep it out of the capture window
 for _ in range(frames):
     s.onRender(ubo)
+    s.synchronize()
 print(s.stats())
