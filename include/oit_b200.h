@@ -85,8 +85,15 @@ typedef struct OitConfig
   uint32_t bandCount;
   uint32_t bandIndex;
   uint32_t stripRows;                     /* multiple of 16; 0 = default (32) */
-  uint32_t reserved[4];
+  uint32_t reserved[4];                   /* [0] bit 0: keep the intermediate images (staged frame); [1]: OIT_CFG_SCENE_STDLIB */
 } OitConfig;
+
+/* Scene generator only: std::default_random_engine / uniform_real_distribution<float> (main.cpp:350-351) are
+   implementation-defined.  libstdc++: minstd_rand0, one draw / (2^31 - 2); MSVC's STL: mt19937, one draw / 2^32 -- the
+   build that produced the screenshot in the reference's doc/ directory (tests/test_reference_screenshot.py). */
+#define OIT_STDLIB_LIBSTDCXX 0u
+#define OIT_STDLIB_MSVC 1u
+#define OIT_CFG_SCENE_STDLIB(cfg) ((cfg)->reserved[1])
 
 /* shaderio::SceneData, std140, 224 bytes (shaders/common.h:77-92); matrices column-major like glm.
    viewport and linkedListAllocatedPerElement are overwritten by the library exactly as

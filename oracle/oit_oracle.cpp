@@ -1,7 +1,8 @@
 /*
  * oit_oracle.cpp -- CPU ORACLE (test infrastructure, see oit_oracle.h): a sequential restatement of the
  * reference's order-independent-transparency hot path, one function per reference shader / host stage.
- * Citations are file:line under /root/reference.  PARITY UNPINNED (see header).
+ * Citations are file:line under /root/reference.  Pinned at image level against the reference's published
+ * screenshot, UNPINNED below that (see header).
  *
  * Schedule: triangles in index order, and per triangle pixels in raster order: a legal schedule
  * of every technique and THE defined result for Loop32, ordered Interlock, Loop64 without tail blend and every
@@ -951,6 +952,40 @@ void compositeInvocation(OracleCtx* c, uint32_t x, uint32_t y, uint32_t sampleID
   }
 }
 
+/* std::mt19937 (the 1998 reference algorithm) + the generate_canonical<float, 24> of MSVC's STL as
+   uniform_real_distribution<float> uses it: ONE 32-bit draw, float(x) / 2^32 (may round up to 1.0f, as MSVC's does) */
+struct Mt19937
+{
+  uint32_t mt[624];
+  int      idx;
+  explicit Mt19937(uint32_t seed)
+  {
+    mt[0] = seed;
+    for(int i = 1; i < 624; i++)
+      mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next()
+  {
+    if(idx >= 624)
+    {
+      for(int k = 0; k < 624; k++)
+      {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7FFFFFFFu);
+        mt[k]            = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9D2C5680u;
+    y ^= (y << 15) & 0xEFC60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  float canonicalMsvc() { return (float)next() / 4294967296.0f; }
+};
+
 }  // namespace
 
 /* ================================================================================================================ */
@@ -963,6 +998,12 @@ float oracle_rand_canonical(uint64_t* state)
   *state        = (*state * 16807ull) % 2147483647ull;
   const float r = (float)(*state - 1) / 2147483646.0f;
   return r >= 1.0f ? nextafterf(1.0f, 0.0f) : r;
+}
+
+int oracle_generate_scene_ex(const OracleConfig* cfg, int stdlib, float* vertices, uint32_t* indices);
+int oracle_generate_scene(const OracleConfig* cfg, float* vertices, uint32_t* indices)
+{
+  return oracle_generate_scene_ex(cfg, 0, vertices, indices);
 }
 
 int oracle_scene_sizes(const OracleConfig* cfg, uint32_t* nVerts, uint32_t* nIndices, uint32_t* indicesPerObject)
@@ -979,7 +1020,7 @@ int oracle_scene_sizes(const OracleConfig* cfg, uint32_t* nVerts, uint32_t* nInd
 
 /* initScene (main.cpp:334-391) with nvutils::createSphereUv(1, 2*subdiv, subdiv) restated (un-vendored nvpro_core2):
    stacks from +z pole to -z pole, (sectors+1) vertices per stack, two triangles per quad except at the poles */
-int oracle_generate_scene(const OracleConfig* cfg, float* vertices, uint32_t* indices)
+int oracle_generate_scene_ex(const OracleConfig* cfg, int stdlib, float* vertices, uint32_t* indices)
 {
   const int   sectors = cfg->subdiv * 2, stacks = cfg->subdiv;
   const float pi = 3.14159265358979323846f;
@@ -1019,9 +1060,14 @@ int oracle_generate_scene(const OracleConfig* cfg, float* vertices, uint32_t* in
   }
   const uint32_t nv = (uint32_t)sp.size() / 3, ni = (uint32_t)st.size();
   uint64_t       rng = 3625;  // main.cpp:350
+  Mt19937        mt(3625u);
+  /* std::default_random_engine is implementation-defined: minstd_rand0 in libstdc++ (stdlib 0), mt19937 in MSVC's STL
+     (stdlib 1 -- the build that produced the screenshot in the reference's doc/, see tests/test_reference_screenshot.py) */
+  auto oracle_rand_canonical = [&](uint64_t* state) -> float { return stdlib == 1 ? mt.canonicalMsvc() : ::oracle_rand_canonical(state); };
   for(int o = 0; o < cfg->numObjects; o++)
   {
-    /* g++ evaluates the constructor arguments at main.cpp:356,366 right to left (probed) */
+    /* g++ and MSVC both evaluate the constructor arguments at main.cpp:356,366 right to left (g++ probed, SURVEY 8c;
+       MSVC confirmed by the screenshot) */
     const float cz = oracle_rand_canonical(&rng), cy = oracle_rand_canonical(&rng), cx = oracle_rand_canonical(&rng);
     const float center[3] = {(cx - 0.5f) * 8.0f, (cy - 0.5f) * 8.0f, (cz - 0.5f) * 8.0f};
     float       radius    = 8.0f * 0.9f / 16;

@@ -89,6 +89,7 @@ def lib():
         L.oracle_buffer_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4
         L.oracle_scene_sizes.argtypes = [C.POINTER(OracleConfig)] + [C.POINTER(C.c_uint32)] * 3
         L.oracle_generate_scene.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_void_p]
+        L.oracle_generate_scene_ex.argtypes = [C.POINTER(OracleConfig), C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_camera.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.c_float, C.c_float, C.POINTER(SceneData)]
         L.oracle_rand_canonical.restype = C.c_float
@@ -116,13 +117,17 @@ def make_config(algorithm=OIT_SPINLOCK, oitLayers=8, linkedListAllocatedPerEleme
                         int(interlockIsOrdered), numObjects, subdiv, scaleMin, scaleWidth, aaType, width, height)
 
 
-def generate_scene(cfg):
+STDLIB_LIBSTDCXX, STDLIB_MSVC = 0, 1
+
+
+def generate_scene(cfg, stdlib=STDLIB_LIBSTDCXX):
+    """initScene; `stdlib` picks whose std::default_random_engine drew the spheres (libstdc++: minstd_rand0, MSVC: mt19937)."""
     nv, ni, ipo = C.c_uint32(), C.c_uint32(), C.c_uint32()
     if lib().oracle_scene_sizes(C.byref(cfg), C.byref(nv), C.byref(ni), C.byref(ipo)) != 0:
         raise ValueError("bad scene parameters")
     verts = np.empty((nv.value, 10), np.float32)
     idx = np.empty(ni.value, np.uint32)
-    lib().oracle_generate_scene(C.byref(cfg), verts.ctypes.data, idx.ctypes.data)
+    lib().oracle_generate_scene_ex(C.byref(cfg), int(stdlib), verts.ctypes.data, idx.ctypes.data)
     return verts, idx, ipo.value
 
 

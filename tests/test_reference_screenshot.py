@@ -1,0 +1,89 @@
+"""Pins the oracle (and the CUDA path) to the reference's OWN output: the screenshot the reference ships in doc/
+(tests/golden/make_reference_screenshot.py explains the fixture).  The capture was made with an MSVC build -- its
+std::default_random_engine is mt19937, not libstdc++'s minstd_rand0 -- so the scene is generated with
+sceneStdlib=MSVC; everything else is the default state the GUI panel shows: Interlock, 16 layers, MSAA 4x pixel shading,
+tail blend, 1024 spheres of subdivision 16, the default camera, a 1920 x 1017 viewport (the capture holds rows 1..1016).
+
+What matches: the scene generator (sphere placement, radii, colours, argument evaluation order), the camera and
+projection, rasterisation and 4x MSAA coverage, the Interlock k-buffer with 16 layers + tail blending, the sort and
+blend arithmetic, sRGB encoding and the MSAA resolve.  Tolerance (the reference ran on a hardware rasteriser / ROP, the
+GLSL compiler contracts multiply-adds, and ties in Interlock's racy ordering may differ): mean absolute difference
+<= 0.5 / 255, >= 65 % of the pixels identical, <= 0.1 % of the pixels off by more than 8 / 255, none by more than 48."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import vk_order_independent_transparency_b200 as oit  # noqa: E402
+from helpers import make_oracle  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_screenshot_interlock16_msaa4.png")
+W, H = 1920, 1017
+GUI_W, GUI_H = 360, 400
+
+
+def screenshot():
+    Image = pytest.importorskip("PIL.Image")
+    img = np.asarray(Image.open(GOLD).convert("RGB")).astype(np.int32)
+    assert img.shape == (H - 1, W, 3)
+    mask = np.ones((H - 1, W), bool)
+    mask[:GUI_H, :GUI_W] = False
+    return img, mask
+
+
+def state():
+    return oit.State(algorithm=oit.OIT_INTERLOCK, oitLayers=16, aaType=oit.AA_MSAA_4X, tailBlend=True, numObjects=1024, subdiv=16,
+                     scaleMin=0.1, scaleWidth=0.9, sceneStdlib=oit.STDLIB_MSVC)
+
+
+def check_against_screenshot(final_bgra):
+    img, mask = screenshot()
+    rgb = oit.bgra_to_rgba_image(final_bgra)[1:, :, :3].astype(np.int32)   # the capture starts at viewport row 1
+    d = np.abs(rgb - img).max(axis=-1)[mask]
+    stats = dict(mean=float(np.abs(rgb - img)[mask].mean()), identical=float((d == 0).mean()), over8=float((d > 8).mean()), worst=int(d.max()))
+    assert stats["mean"] <= 0.5 and stats["identical"] >= 0.65 and stats["over8"] <= 1e-3 and stats["worst"] <= 48, stats
+    return stats
+
+
+def test_oracle_reproduces_the_reference_screenshot():
+    from oracle import oracle_py as O
+    st = state()
+    verts, idx, ipo = oit.generate_scene(st)
+    # the oracle's own generator (independent code) draws the same MSVC scene
+    overts, oidx, _ = O.generate_scene(O.make_config(numObjects=1024, subdiv=16), O.STDLIB_MSVC)
+    assert np.array_equal(verts, overts) and np.array_equal(idx, oidx)
+    o, sd = make_oracle(O, st, W, H, verts, idx, ipo, oit.default_camera(W, H), os.cpu_count() or 1)
+    o.render(sd)
+    assert o.abuffer.nbytes == 499875840      # "A-buffer: 499875840 bytes" in the capture's GUI panel
+    stats = check_against_screenshot(o.final)
+    print("oracle vs reference screenshot:", stats)
+    # the wrong standard library's random engine must NOT match: the check discriminates
+    st2 = oit.State(algorithm=5, oitLayers=16, aaType=1)
+    v2, i2, ipo2 = oit.generate_scene(st2)
+    o2, sd2 = make_oracle(O, st2, W, H, v2, i2, ipo2, oit.default_camera(W, H), os.cpu_count() or 1)
+    o2.render(sd2)
+    with pytest.raises(AssertionError):
+        check_against_screenshot(o2.final)
+    o.close()
+    o2.close()
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_the_reference_screenshot():
+    from oracle import oracle_py as O
+    st = state()
+    verts, idx, ipo = oit.generate_scene(st)
+    ubo = oit.default_camera(W, H)
+    s = oit.Sample(st, W, H)
+    s.setScene(verts, idx, ipo)
+    s.onRender(ubo)
+    fin = s.readColor()
+    assert s.buffer_size(oit.BUF_ABUFFER) == 499875840
+    print("CUDA vs reference screenshot:", check_against_screenshot(fin))
+    o, sd = make_oracle(O, st, W, H, verts, idx, ipo, ubo, os.cpu_count() or 1)
+    o.render(sd)
+    assert np.array_equal(fin, o.final)        # and bit-identical to the oracle, as everywhere else
+    s.close()
+    o.close()

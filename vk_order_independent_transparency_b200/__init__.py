@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "oit_band_peer_disable", "oit_generate_spheres", "oit_set_scene_spheres",
 ]
 BUF_FRAME = 10
+STDLIB_LIBSTDCXX, STDLIB_MSVC = 0, 1  # OIT_CFG_SCENE_STDLIB: minstd_rand0 (libstdc++) or mt19937 (MSVC) scene RNG
 
 
 class OitError(RuntimeError):
@@ -129,7 +130,8 @@ class State:
 
     def __init__(self, algorithm=OIT_SPINLOCK, oitLayers=8, linkedListAllocatedPerElement=10, percentTransparent=100,
                  tailBlend=True, interlockIsOrdered=True, numObjects=1024, subdiv=16, scaleMin=0.1, scaleWidth=0.9,
-                 aaType=AA_NONE):
+                 aaType=AA_NONE, sceneStdlib=STDLIB_LIBSTDCXX):
+        self.sceneStdlib = sceneStdlib  # harness only: whose std::default_random_engine draws the scene (see oit_b200.h)
         self.algorithm = algorithm
         self.oitLayers = oitLayers
         self.linkedListAllocatedPerElement = linkedListAllocatedPerElement
@@ -162,6 +164,7 @@ class State:
         cfg.numObjects, cfg.subdiv, cfg.scaleMin, cfg.scaleWidth = self.numObjects, self.subdiv, self.scaleMin, self.scaleWidth
         cfg.aaType, cfg.width, cfg.height, cfg.device = self.aaType, width, height, device
         cfg.bandCount, cfg.bandIndex, cfg.stripRows = bandCount, bandIndex, stripRows
+        cfg.reserved[1] = int(self.sceneStdlib)
         return cfg
 
 

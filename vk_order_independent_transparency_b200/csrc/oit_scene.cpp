@@ -25,6 +25,40 @@ struct MinStd
   }
 };
 
+// std::mt19937 + MSVC's generate_canonical<float, 24> (one 32-bit draw / 2^32, may round up to 1.0f): what
+// std::default_random_engine and uniform_real_distribution<float> are in MSVC's STL (OIT_STDLIB_MSVC)
+struct Mt19937
+{
+  uint32_t state[624];
+  int      pos = 624;
+  explicit Mt19937(uint32_t seed)
+  {
+    state[0] = seed;
+    for(uint32_t i = 1; i < 624; i++)
+      state[i] = 1812433253u * (state[i - 1] ^ (state[i - 1] >> 30)) + i;
+  }
+  void twist()
+  {
+    for(int i = 0; i < 624; i++)
+    {
+      const uint32_t mixed = (state[i] & 0x80000000u) | (state[(i + 1) % 624] & 0x7FFFFFFFu);
+      state[i]             = state[(i + 397) % 624] ^ (mixed >> 1) ^ ((mixed & 1u) ? 0x9908B0DFu : 0u);
+    }
+    pos = 0;
+  }
+  float next()
+  {
+    if(pos >= 624)
+      twist();
+    uint32_t v = state[pos++];
+    v ^= v >> 11;
+    v ^= (v << 7) & 0x9D2C5680u;
+    v ^= (v << 15) & 0xEFC60000u;
+    v ^= v >> 18;
+    return (float)v / 4294967296.0f;
+  }
+};
+
 struct UnitSphere
 {
   std::vector<float>    pos;  // xyz per vertex (== normal)
@@ -88,7 +122,16 @@ int oit_generate_spheres(const OitConfig* cfg, OitSphere* spheres)
 {
   if(!spheres || oit_scene_sizes(cfg, nullptr, nullptr, nullptr) != OIT_OK)
     return OIT_ERR_INVALID_ARG;
-  MinStd      rng{3625};                          // main.cpp:350
+  MinStd      minstd{3625};  // main.cpp:350
+  Mt19937     mt(3625u);
+  const bool  msvc = OIT_CFG_SCENE_STDLIB(cfg) == OIT_STDLIB_MSVC;
+  struct
+  {
+    MinStd&  a;
+    Mt19937& b;
+    bool     useB;
+    float    next() { return useB ? b.next() : a.next(); }
+  } rng{minstd, mt, msvc};
   const float kGlobalScale = 8.0f, kGrid = 16.0f;  // GLOBAL_SCALE, GRID_SIZE (main.cpp:54-55)
   for(int obj = 0; obj < cfg->numObjects; obj++)
   {
