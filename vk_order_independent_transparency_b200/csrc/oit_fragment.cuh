@@ -402,16 +402,33 @@ __device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, int pl, uin
   c.nStored++;
 }
 
-template <int S>
+// Code that most frames never execute (the tail-blend ROP, 64-bit coverage of huge triangles, the per-sample depth test
+// against opaque geometry) is kept out of line: the frame kernel is instruction-cache bound (ncu: "no instruction" stalls),
+// and inlined S-times-unrolled copies of these paths sat in the middle of its hot loops.
+#ifndef OIT_COLD_NOINLINE
+#define OIT_COLD_NOINLINE 1
+#endif
+#if OIT_COLD_NOINLINE
+#define OIT_COLD __noinline__
+#else
+#define OIT_COLD __forceinline__
+#endif
+
 // px: the S colour samples of the pixel -- in m_colorImage, or in the shared-memory tile of the fused frame kernel
+template <int S>
+__device__ OIT_COLD void ropSamplesNonZero(const SrgbTables& t, uint32_t* px, uint32_t mask, Color4 src)
+{
+#pragma unroll 1
+  for(int s = 0; s < S; s++)
+    if(mask & (1u << s))
+      px[s] = ropPremult(t, px[s], src);
+}
+template <int S>
 __device__ __forceinline__ void ropSamples(const FragCtx& c, uint32_t* px, uint32_t mask, const Color4& src)
 {
   if(isZero(src))
     return;  // identity blend: encode(decode(v)) == v for every 8-bit v
-#pragma unroll
-  for(int s = 0; s < S; s++)
-    if(mask & (1u << s))
-      px[s] = ropPremult(c.t, px[s], src);
+  ropSamplesNonZero<S>(c.t, px, mask, src);
 }
 
 // the part of an invocation that does not depend on the shaded colour: issued first so that its memory latency is

@@ -113,14 +113,15 @@ struct AbufView
 };
 
 // pix: the pixel's index inside that slice
-template <int S>
+// ALG: the technique, a compile-time constant of the kernel instance (the other techniques' code is not instantiated)
+template <int S, int ALG>
 __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, const AbufView& av,
                                                            size_t pix, int sampleID)
 {
   const size_t P = av.viewSize;
   const int    L = p.L;
   const size_t ai = (size_t)sampleID * P + pix;
-  switch(p.algorithm)
+  switch(ALG)
   {
     case OIT_SIMPLE:
     case OIT_SPINLOCK:
@@ -202,12 +203,12 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
 
 // composite (+ its ROP onto the shared-memory colour tile) of the tile pixel owned by thread t
 // wAcc / wRev: the pixel's S WBOIT accumulator / revealage samples (shared-memory tile), only used for OIT_WEIGHTED
-template <int S>
+template <int S, int ALG>
 __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, const AbufView& av,
                                                     size_t pixA, size_t pix, uint32_t* px, const uint2* wAcc = nullptr,
                                                     const uint16_t* wRev = nullptr)
 {
-  if(p.algorithm == OIT_WEIGHTED)
+  if(ALG == OIT_WEIGHTED)
   {
     // K16 oitWeighted.frag.glsl:98-109 + BlendMode::WEIGHTED_COMPOSITE, per sample
 #pragma unroll 1
@@ -229,13 +230,13 @@ __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const 
 #pragma unroll 1
     for(int s = 0; s < S; s++)
     {
-      const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, av, pixA, s);
+      const Color4 out = fusedCompositeInvocation<S, ALG>(p, tb, A, t, av, pixA, s);
       if(!isZero(out))
         px[s] = ropPremult(tb, px[s], out);
     }
     return;
   }
-  const Color4 out = fusedCompositeInvocation<S>(p, tb, A, t, av, pixA, 0);
+  const Color4 out = fusedCompositeInvocation<S, ALG>(p, tb, A, t, av, pixA, 0);
   if(isZero(out))
     return;
   uint32_t prevDst = px[0], prevRes = ropPremult(tb, prevDst, out);

@@ -57,12 +57,16 @@ struct SamplePattern<1>
 {
   static __device__ __forceinline__ int x(int) { return 128; }
   static __device__ __forceinline__ int y(int) { return 128; }
+  static __device__ __forceinline__ int xr(int) { return 128; }  // xr / yr: the same for a run-time sample index
+  static __device__ __forceinline__ int yr(int) { return 128; }
 };
 template <>
 struct SamplePattern<4>
 {
   static __device__ __forceinline__ int x(int s) { return s == 0 ? 96 : s == 1 ? 224 : s == 2 ? 32 : 160; }
   static __device__ __forceinline__ int y(int s) { return s == 0 ? 32 : s == 1 ? 96 : s == 2 ? 160 : 224; }
+  static __device__ __forceinline__ int xr(int s) { return (int)((0xA020E060u >> (8 * s)) & 255u); }
+  static __device__ __forceinline__ int yr(int s) { return (int)((0xE0A06020u >> (8 * s)) & 255u); }
 };
 template <>
 struct SamplePattern<8>
@@ -75,6 +79,8 @@ struct SamplePattern<8>
   {
     return s == 0 ? 80 : s == 1 ? 176 : s == 2 ? 144 : s == 3 ? 48 : s == 4 ? 208 : s == 5 ? 112 : s == 6 ? 240 : 16;
   }
+  static __device__ __forceinline__ int xr(int s) { return (int)((0xF0B0103050D07090ull >> (8 * s)) & 255ull); }
+  static __device__ __forceinline__ int yr(int s) { return (int)((0x10F070D03090B050ull >> (8 * s)) & 255ull); }
 };
 
 // c + lo16(a) * byte0(b) + hi16(a) * byte1(b), a signed halves, b unsigned bytes (SASS IDP.2A.LO.S16.U8)
@@ -97,6 +103,53 @@ __device__ __forceinline__ float edgeFloat(const TriSlot& s, int q, int px, int 
 }
 
 // post-depth coverage mask of pixel (gx, gy) [global], depth samples at dpx (or nullptr = cleared to 1.0)
+// coverage of a triangle too large for the int32 / IDP.2A path (extent > 64 px): rare, kept out of line
+template <int S>
+__device__ OIT_COLD uint32_t coverageMaskLarge(const TriSlot& s, int ox, int oy)
+{
+  uint32_t  mask = 0;
+  long long e[3];
+  int       dxs[3], dys[3];
+#pragma unroll
+  for(int q = 0; q < 3; q++)
+  {
+    const int a = (q + 1) % 3, b = (q + 2) % 3;
+    dxs[q]      = s.x[b] - s.x[a];
+    dys[q]      = s.y[b] - s.y[a];
+    e[q]        = (long long)dxs[q] * (oy - s.y[a]) - (long long)dys[q] * (ox - s.x[a]) - (long long)((s.box >> (16 + q)) & 1u);
+  }
+#pragma unroll 1
+  for(int sI = 0; sI < S; sI++)
+  {
+    const int       sx = SamplePattern<S>::xr(sI), sy = SamplePattern<S>::yr(sI);
+    const long long e0 = e[0] + (long long)dxs[0] * sy - (long long)dys[0] * sx;
+    const long long e1 = e[1] + (long long)dxs[1] * sy - (long long)dys[1] * sx;
+    const long long e2 = e[2] + (long long)dxs[2] * sy - (long long)dys[2] * sx;
+    if((e0 | e1 | e2) >= 0)
+      mask |= 1u << sI;
+  }
+  return mask;
+}
+
+// early per-sample depth test, VK_COMPARE_OP_LESS (main.cpp:530-532): only runs when opaque geometry was drawn or a vertex
+// depth is not safely below the clear value 1.0
+template <int S>
+__device__ OIT_COLD uint32_t depthTestMask(const TriSlot& s, int ox, int oy, const float* dpx, uint32_t mask)
+{
+  const bool small = (s.box >> 20) & 1u;
+#pragma unroll 1
+  for(int sI = 0; sI < S; sI++)
+    if(mask & (1u << sI))
+    {
+      const int   px = ox + SamplePattern<S>::xr(sI), py = oy + SamplePattern<S>::yr(sI);
+      const Bary  b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
+      const float zs = depthAt(s, b);
+      if(!(zs < (dpx ? dpx[sI] : 1.0f)))
+        mask &= ~(1u << sI);
+    }
+  return mask;
+}
+
 template <int S>
 __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int gy, const float* dpx)
 {
@@ -135,43 +188,9 @@ __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int g
     }
   }
   else
-  {
-    long long e[3];
-    int       dxs[3], dys[3];
-#pragma unroll
-    for(int q = 0; q < 3; q++)
-    {
-      const int a = (q + 1) % 3, b = (q + 2) % 3;
-      dxs[q]      = s.x[b] - s.x[a];
-      dys[q]      = s.y[b] - s.y[a];
-      e[q]        = (long long)dxs[q] * (oy - s.y[a]) - (long long)dys[q] * (ox - s.x[a]) - (long long)((s.box >> (16 + q)) & 1u);
-    }
-#pragma unroll
-    for(int sI = 0; sI < S; sI++)
-    {
-      const int       sx = SamplePattern<S>::x(sI), sy = SamplePattern<S>::y(sI);
-      const long long e0 = e[0] + (long long)dxs[0] * sy - (long long)dys[0] * sx;
-      const long long e1 = e[1] + (long long)dxs[1] * sy - (long long)dys[1] * sx;
-      const long long e2 = e[2] + (long long)dxs[2] * sy - (long long)dys[2] * sx;
-      if((e0 | e1 | e2) >= 0)
-        mask |= 1u << sI;
-    }
-  }
+    mask = coverageMaskLarge<S>(s, ox, oy);
   if(mask && (dpx != nullptr || !zSafe))
-  {
-    // early per-sample depth test, VK_COMPARE_OP_LESS (main.cpp:530-532); skipped when the depth buffer is the clear
-    // value 1.0 and every vertex depth is safely below it
-#pragma unroll
-    for(int sI = 0; sI < S; sI++)
-      if(mask & (1u << sI))
-      {
-        const int   px = ox + SamplePattern<S>::x(sI), py = oy + SamplePattern<S>::y(sI);
-        const Bary  b  = makeBary(edgeFloat(s, 1, px, py, small), edgeFloat(s, 2, px, py, small), s.rarea);
-        const float zs = depthAt(s, b);
-        if(!(zs < (dpx ? dpx[sI] : 1.0f)))
-          mask &= ~(1u << sI);
-      }
-  }
+    mask = depthTestMask<S>(s, ox, oy, dpx, mask);
   return mask;
 }
 
@@ -248,6 +267,19 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
 #ifndef OIT_MIN_BLOCKS
 #define OIT_MIN_BLOCKS 5
 #endif
+// the technique a colour pass belongs to (the fused composite is specialised on it)
+__host__ __device__ constexpr int passAlgorithm(int pass)
+{
+  return pass == PASS_SIMPLE ? OIT_SIMPLE
+       : pass == PASS_LINKEDLIST ? OIT_LINKEDLIST
+       : pass == PASS_LOOP_COLOR ? OIT_LOOP
+       : pass == PASS_LOOP64 ? OIT_LOOP64
+       : pass == PASS_SPINLOCK ? OIT_SPINLOCK
+       : pass == PASS_INTERLOCK ? OIT_INTERLOCK
+       : pass == PASS_WEIGHTED ? OIT_WEIGHTED
+                               : -1;
+}
+
 template <int PASS, int S, bool SSHADE>
 __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const FrameParams p)
 {
@@ -570,7 +602,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
       {
         const AbufView av{ctx.abuf, ctx.aux, ctx.viewSize};
         const size_t   pixG = (size_t)(yLocal0 + ly) * p.W + gx;
-        fusedCompositePixel<S>(p, tabs, A, pl, av, ctx.onChip ? (size_t)pl : pixG, pixG, tileColorSm + pl * S,
+        fusedCompositePixel<S, passAlgorithm(PASS)>(p, tabs, A, pl, av, ctx.onChip ? (size_t)pl : pixG, pixG, tileColorSm + pl * S,
                                WEIGHTED ? wAccSm + pl * S : nullptr, WEIGHTED ? wRevSm + pl * S : nullptr);
       }
     }
