@@ -84,7 +84,16 @@ __device__ __forceinline__ Color4 decodeDst(const SrgbTables& t, uint32_t d)
 {
   return Color4{t.dec[(d >> 16) & 255], t.dec[(d >> 8) & 255], t.dec[d & 255], t.a255[d >> 24]};
 }
+// One copy per kernel instead of one per call site (OIT_SHARE_ENCODE): three enc8 are ~75 SASS instructions, the frame
+// kernel has a dozen call sites (ROP, composite, resolve) and is instruction-cache bound; the call costs less than the misses.
+#ifndef OIT_SHARE_ENCODE
+#define OIT_SHARE_ENCODE 1
+#endif
+#if OIT_SHARE_ENCODE
+static __device__ __noinline__ uint32_t encodeDst(const SrgbTables& t, Color4 c)
+#else
 __device__ __forceinline__ uint32_t encodeDst(const SrgbTables& t, const Color4& c)
+#endif
 {
   return enc8(t, c.b) | (enc8(t, c.g) << 8) | (enc8(t, c.r) << 16) | (unorm8(c.a) << 24);
 }

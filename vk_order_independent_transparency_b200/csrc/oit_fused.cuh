@@ -12,6 +12,10 @@ namespace oit {
 
 constexpr int FUSED_LCAP = 8;  // the fused frame kernel is used for OIT_LAYERS <= 8; larger values take the staged kernels
 
+#ifndef OIT_COMPACT_COMPOSITE
+#define OIT_COMPACT_COMPOSITE 1
+#endif
+
 struct FusedArrays
 {
   uint32_t c[FUSED_LCAP][TILE_PIX];
@@ -76,6 +80,9 @@ __device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedAr
 #pragma unroll
     for(int s = 0; s < S; s++)
       sc[s] = zeroColor();
+#if OIT_COMPACT_COMPOSITE
+#pragma unroll 1  // the S-wide body is big enough: unrolling over the fragments only costs instruction-cache space
+#endif
     for(int i = 0; i < n; i++)
     {
       const Color4   pm = premultiply(unpackColor(tb, A.c[i][t]));

@@ -329,19 +329,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
     }
   };
   uint32_t* tileColor = (fused && !WEIGHTED) ? tileColorSm : nullptr;
+  // fused frame, nothing transparent touches this tile: only the resolve of what is there runs (same code as below)
+  const bool emptyTile = listBegin == listEnd;
   if(fused)
   {
-    if(!WEIGHTED || listBegin == listEnd)
+    if(!WEIGHTED || emptyTile)
       initColorTile();
-    if(listBegin == listEnd)
-    {
-      // nothing transparent touches this tile: resolve what is there
-      loadTables(tabs, p.tables);
-      __syncthreads();
-      fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
-      return;
-    }
-    if(WEIGHTED)
+    if(WEIGHTED && !emptyTile)
       for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
       {
         wAccSm[i] = make_uint2(0u, 0u);  // accum cleared to 0, reveal to 1.0 (oitRender.cpp:394-397)
@@ -349,15 +343,16 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
       }
   }
   loadTables(tabs, p.tables);
-  for(int i = tid; i < TILE_PIX * MASK_WORDS; i += RASTER_THREADS)
-    pixMask[i] = 0u;
+  if(!emptyTile)
+    for(int i = tid; i < TILE_PIX * MASK_WORDS; i += RASTER_THREADS)
+      pixMask[i] = 0u;
   layerCount[0][tid] = 0u;
   layerCount[1][tid] = 0u;
   if(tid < 2)
     numLayers[tid] = 0u;
   FragCtx ctx{p, tabs, 0, 0, 0, 0, (fused && WEIGHTED) ? wAccSm : nullptr, (fused && WEIGHTED) ? wRevSm : nullptr,
               p.abuf, p.aux, p.adepth, p.spin, (size_t)p.W * p.localH, false};
-  if(fused && p.onChip && !WEIGHTED)
+  if(fused && p.onChip && !WEIGHTED && !emptyTile)
   {
     // the tile's k-buffer slice + aux words in shared memory, behind the colour tile: [A-buffer][imgAux][imgDepth][imgSpin],
     // cleared like clearTransparent{Simple,Loop64,Lock} clear the global ones (oitRender.cpp:156-174,303-311,337-356)
@@ -587,23 +582,26 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
   // ---- fused frame: composite + resolve of the tile while its A-buffer slice is still in L1 / L2 --------------------------
   if(fused)
   {
-    FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
-    __threadfence_block();
-    __syncthreads();
-    if(WEIGHTED)
+    if(!emptyTile)
     {
-      initColorTile();  // into the scratch area, which the chunk structures no longer need
+      FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
+      __threadfence_block();
       __syncthreads();
-    }
-    for(int pl = tid; pl < TILE_PIX; pl += RASTER_THREADS)
-    {
-      const int gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
-      if(gx < p.W && tileY0 + ly < p.H)
+      if(WEIGHTED)
       {
-        const AbufView av{ctx.abuf, ctx.aux, ctx.viewSize};
-        const size_t   pixG = (size_t)(yLocal0 + ly) * p.W + gx;
-        fusedCompositePixel<S, passAlgorithm(PASS)>(p, tabs, A, pl, av, ctx.onChip ? (size_t)pl : pixG, pixG, tileColorSm + pl * S,
-                               WEIGHTED ? wAccSm + pl * S : nullptr, WEIGHTED ? wRevSm + pl * S : nullptr);
+        initColorTile();  // into the scratch area, which the chunk structures no longer need
+        __syncthreads();
+      }
+      for(int pl = tid; pl < TILE_PIX; pl += RASTER_THREADS)
+      {
+        const int gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
+        if(gx < p.W && tileY0 + ly < p.H)
+        {
+          const AbufView av{ctx.abuf, ctx.aux, ctx.viewSize};
+          const size_t   pixG = (size_t)(yLocal0 + ly) * p.W + gx;
+          fusedCompositePixel<S, passAlgorithm(PASS)>(p, tabs, A, pl, av, ctx.onChip ? (size_t)pl : pixG, pixG, tileColorSm + pl * S,
+                                                      WEIGHTED ? wAccSm + pl * S : nullptr, WEIGHTED ? wRevSm + pl * S : nullptr);
+        }
       }
     }
     __syncthreads();
