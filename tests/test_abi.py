@@ -95,3 +95,15 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower().replace("oracle's", ""), f
+
+
+def test_save_png_roundtrip(oit_mod, tmp_path):
+    """save_png (the sequencer's saveImageToFile, main.cpp:887-891) writes the frame's bytes unchanged: BGRA -> RGBA PNG."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(7)
+    frame = rng.integers(0, 2**32, size=(37, 53), dtype=np.uint64).astype(np.uint32)
+    path = tmp_path / "frame.png"
+    oit_mod.save_png(frame, str(path))
+    back = np.asarray(Image.open(path))
+    assert back.shape == (37, 53, 4) and back.dtype == np.uint8
+    assert np.array_equal(back, oit_mod.bgra_to_rgba_image(frame))

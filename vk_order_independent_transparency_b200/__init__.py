@@ -354,6 +354,10 @@ class Sample:
     def synchronize(self):
         self._check(self.L.oit_synchronize(self.h))
 
+    def saveImage(self, path):
+        """saveImageToFile of the test sequencer (main.cpp:887-891): this band's frame as a PNG."""
+        save_png(self.readColor(), path)
+
     # ---- results ------------------------------------------------------------------------------------------------------
     def buffer_size(self, which):
         n = C.c_size_t()
@@ -458,3 +462,22 @@ class Sample:
 def bgra_to_rgba_image(final):
     b = np.ascontiguousarray(final).view(np.uint8).reshape(final.shape[0], final.shape[1], 4)
     return b[..., [2, 1, 0, 3]].copy()
+
+
+def save_png(final, path):
+    """What the reference's test sequencer does with m_viewportImage after every sequence (saveImageToFile,
+    main.cpp:887-891): the BGRA8 frame (`Sample.readColor()` / `readFrame()`) as an 8-bit RGBA PNG.  Dependency-free
+    (zlib + struct); the bytes are the sRGB-encoded values the frame holds, written unchanged."""
+    import struct
+    import zlib
+    rgba = bgra_to_rgba_image(final)
+    h, w = rgba.shape[:2]
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), rgba.reshape(h, w * 4)], axis=1).tobytes()   # filter type 0 per row
+
+    def chunk(tag, data):
+        body = tag + data
+        return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
