@@ -1,0 +1,22 @@
+"""Small frames of several techniques for compute-sanitizer runs (memcheck / racecheck / initcheck):
+compute-sanitizer --tool racecheck python tools/sanitize_frame.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vk_order_independent_transparency_b200 as oit  # noqa: E402
+
+W, H = 112, 80
+CASES = [dict(algorithm=1, aaType=4), dict(algorithm=3, aaType=0), dict(algorithm=4, aaType=2), dict(algorithm=6, aaType=1),
+         dict(algorithm=2, aaType=3), dict(algorithm=5, aaType=1, percentTransparent=50), dict(algorithm=0, aaType=5)]
+for kw in CASES:
+    st = oit.State(numObjects=24, subdiv=5, **kw)
+    s = oit.Sample(st, W, H)
+    s.initScene()
+    ubo = oit.default_camera(W, H)
+    for _ in range(2):
+        s.onRender(ubo)
+    s.synchronize()
+    print(kw, s.stats()["fragments"], flush=True)
+    s.close()
+print("done")
