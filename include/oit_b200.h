@@ -118,7 +118,8 @@ typedef struct OitStats
   uint64_t fragmentsTail;
   uint64_t opaqueFragments;
   uint64_t trianglesDrawn;
-  uint64_t trianglesRejected;  /* w<=0, outside the guard band or the depth clip volume */
+  uint64_t trianglesRejected;  /* entirely behind the near plane, or not representable (far plane, guard band);
+                                  triangles that CROSS the near plane are clipped, not rejected */
   uint64_t llCounter;          /* linked list: final counter value (may exceed the pool) */
   uint64_t tilePairs;          /* (tile, triangle) pairs binned this frame */
   uint64_t kernelLaunches;     /* kernels launched by the last oit_render */

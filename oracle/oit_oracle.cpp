@@ -251,6 +251,37 @@ struct OracleCtx
 
 namespace {
 
+/* the vertex stage after the matrix product: perspective divide, viewport transform (main.cpp:507-510), guard band,
+   snapping to 1/256 px */
+TVert finishVertex(const float clip[4], float viewz, float hw, float hh)
+{
+  TVert t;
+  t.viewz = viewz;
+  t.valid = clip[3] > 0.f && clip[3] < std::numeric_limits<float>::infinity();
+  t.x = t.y = 0;
+  t.z = t.invw = 0.f;
+  if(t.valid)
+  {
+    t.invw         = 1.0f / clip[3];
+    const float nx = clip[0] * t.invw, ny = clip[1] * t.invw;
+    t.z            = clip[2] * t.invw;
+    const float xs = fmaf(nx, hw, hw), ys = fmaf(ny, hh, hh);
+    if(!(fabsf(xs) < 2097152.f) || !(fabsf(ys) < 2097152.f) || !(t.z >= 0.f) || !(t.z <= 1.f))
+      t.valid = false;  // outside the guard band / depth clip volume
+    else
+    {
+      t.x = (int32_t)rintf(xs * 256.0f);
+      t.y = (int32_t)rintf(ys * 256.0f);
+    }
+  }
+  if(!t.valid)
+  {
+    t.x = t.y = 0;
+    t.z = t.invw = 0.f;
+  }
+  return t;
+}
+
 /* ---- vertex stage: object.vert.glsl:32-38 + viewport transform (main.cpp:507-510) ------------------------- */
 void transformVertices(OracleCtx* c)
 {
@@ -266,25 +297,8 @@ void transformVertices(OracleCtx* c)
     float        clip[4];
     for(int r = 0; r < 4; r++)
       clip[r] = fmaf(M[0 + r], p[0], fmaf(M[4 + r], p[1], fmaf(M[8 + r], p[2], M[12 + r])));
-    TVert t;
-    t.viewz = fmaf(V[0 + 2], p[0], fmaf(V[4 + 2], p[1], fmaf(V[8 + 2], p[2], V[12 + 2])));
-    t.valid = clip[3] > 0.f && clip[3] < std::numeric_limits<float>::infinity();
-    t.x = t.y = 0;
-    t.z = t.invw = 0.f;
-    if(t.valid)
-    {
-      t.invw         = 1.0f / clip[3];
-      const float nx = clip[0] * t.invw, ny = clip[1] * t.invw;
-      t.z            = clip[2] * t.invw;
-      const float xs = fmaf(nx, hw, hw), ys = fmaf(ny, hh, hh);
-      if(!(fabsf(xs) < 2097152.f) || !(fabsf(ys) < 2097152.f) || !(t.z >= 0.f) || !(t.z <= 1.f))
-        t.valid = false;  // outside the guard band / depth clip volume: triangle is rejected
-      else
-      {
-        t.x = (int32_t)rintf(xs * 256.0f);
-        t.y = (int32_t)rintf(ys * 256.0f);
-      }
-    }
+    const float viewz = fmaf(V[0 + 2], p[0], fmaf(V[4 + 2], p[1], fmaf(V[8 + 2], p[2], V[12 + 2])));
+    const TVert t     = finishVertex(clip, viewz, hw, hh);
     c->tv[i] = t;
   }
 }
@@ -613,22 +627,16 @@ struct Tri
 
 inline bool topLeft(int64_t dx, int64_t dy) { return (dy == 0 && dx > 0) || dy < 0; }
 
-/* mode: 0 = opaque, 1 = transparent depth pass (Loop32), 2 = transparent colour pass */
-bool setupTri(const OracleCtx* c, uint32_t i0, uint32_t i1, uint32_t i2, bool cullBack, Tri& t, ThreadStats& st)
+/* triangle set-up from three post-projection vertices and their attribute records (pos3, normal3, colour4) */
+bool setupTriFrom(const TVert* const v[3], const float* const attr[3], bool cullBack, Tri& t)
 {
-  const TVert &v0 = c->tv[i0], &v1 = c->tv[i1], &v2 = c->tv[i2];
-  if(!v0.valid || !v1.valid || !v2.valid)
-  {
-    st.rejected++;
-    return false;
-  }
-  int64_t area2 = ((int64_t)v1.x - v0.x) * ((int64_t)v2.y - v0.y) - ((int64_t)v2.x - v0.x) * ((int64_t)v1.y - v0.y);
+  int64_t area2 = ((int64_t)v[1]->x - v[0]->x) * ((int64_t)v[2]->y - v[0]->y) - ((int64_t)v[2]->x - v[0]->x) * ((int64_t)v[1]->y - v[0]->y);
   if(area2 == 0)
     return false;
   /* Vulkan: a = -1/2 sum(x_i*y_i+1 - x_i+1*y_i); positive = front for COUNTER_CLOCKWISE => front iff area2 < 0 */
   if(cullBack && area2 > 0)
     return false;
-  uint32_t o[3] = {i0, i1, i2};
+  int o[3] = {0, 1, 2};
   if(area2 < 0)
   {
     std::swap(o[1], o[2]);
@@ -636,13 +644,13 @@ bool setupTri(const OracleCtx* c, uint32_t i0, uint32_t i1, uint32_t i2, bool cu
   }
   for(int k = 0; k < 3; k++)
   {
-    const TVert& v = c->tv[o[k]];
-    t.x[k]         = v.x;
-    t.y[k]         = v.y;
-    t.z[k]         = v.z;
-    t.iw[k]        = v.invw;
-    t.vz[k]        = v.viewz;
-    t.a[k]         = &c->verts[(size_t)o[k] * 10];
+    const TVert& tv = *v[o[k]];
+    t.x[k]          = tv.x;
+    t.y[k]          = tv.y;
+    t.z[k]          = tv.z;
+    t.iw[k]         = tv.invw;
+    t.vz[k]         = tv.viewz;
+    t.a[k]          = attr[o[k]];
   }
   t.area2 = area2;
   /* edge k is opposite vertex k: from vertex k+1 to vertex k+2 */
@@ -653,6 +661,104 @@ bool setupTri(const OracleCtx* c, uint32_t i0, uint32_t i1, uint32_t i2, bool cu
   }
   return true;
 }
+
+/* Near-plane clipping (the fixed-function clipper, 0 <= z_clip) of a triangle with a vertex behind the
+   near plane.  Rules (the CUDA side states the same ones in csrc/oit_clip.cuh):
+    - inside iff z_clip >= 0, clip coordinates from the vertex stage's fma chain;
+    - a new vertex lies on an edge from an INSIDE vertex P to an OUTSIDE vertex Q, always computed in that direction:
+      t = zP / (zP - zQ); x, y, w, view-z and the attributes = fma(t, Q - P, P); z_clip := 0;
+    - one vertex outside (k; a = k+1, b = k+2): A' on a->k, B' on b->k, pieces (A', a, b) and (A', b, B');
+      two outside (inside a; b = a+1, c = a+2): P on a->b, Q on a->c, piece (a, P, Q);
+    - any vertex not representable afterwards (w <= 0, guard band, z outside [0,1]) => the triangle stays rejected. */
+struct ClipPiece
+{
+  TVert v[3];
+  float attr[3][10];
+};
+int clipTriangleNear(const OracleCtx* c, const uint32_t ix[3], ClipPiece out[2])
+{
+  const float* M  = c->ubo.projViewMatrix;
+  const float* V  = c->ubo.viewMatrix;
+  const float  hw = 0.5f * (float)c->W, hh = 0.5f * (float)c->H;
+  float        clip[3][4], vz[3];
+  int          nIn = 0, firstOut = -1, firstIn = -1;
+  for(int k = 0; k < 3; k++)
+  {
+    const float* p = &c->verts[(size_t)ix[k] * 10];
+    for(int r = 0; r < 4; r++)
+      clip[k][r] = fmaf(M[0 + r], p[0], fmaf(M[4 + r], p[1], fmaf(M[8 + r], p[2], M[12 + r])));
+    vz[k] = fmaf(V[0 + 2], p[0], fmaf(V[4 + 2], p[1], fmaf(V[8 + 2], p[2], V[12 + 2])));
+    if(clip[k][2] >= 0.f)
+    {
+      nIn++;
+      if(firstIn < 0)
+        firstIn = k;
+    }
+    else if(firstOut < 0)
+      firstOut = k;
+  }
+  if(nIn == 0 || nIn == 3)
+    return 0;
+  struct CV
+  {
+    TVert v;
+    float attr[10];
+  };
+  auto original = [&](int k) {
+    CV cv;
+    cv.v = finishVertex(clip[k], vz[k], hw, hh);
+    memcpy(cv.attr, &c->verts[(size_t)ix[k] * 10], sizeof(cv.attr));
+    return cv;
+  };
+  auto cut = [&](int in, int outV) {
+    const float zP = clip[in][2], zQ = clip[outV][2];
+    const float t  = zP / (zP - zQ);
+    float       c4[4];
+    c4[0] = fmaf(t, clip[outV][0] - clip[in][0], clip[in][0]);
+    c4[1] = fmaf(t, clip[outV][1] - clip[in][1], clip[in][1]);
+    c4[2] = 0.f;
+    c4[3] = fmaf(t, clip[outV][3] - clip[in][3], clip[in][3]);
+    CV cv;
+    cv.v             = finishVertex(c4, fmaf(t, vz[outV] - vz[in], vz[in]), hw, hh);
+    const float* aP = &c->verts[(size_t)ix[in] * 10];
+    const float* aQ = &c->verts[(size_t)ix[outV] * 10];
+    for(int k = 0; k < 10; k++)
+      cv.attr[k] = fmaf(t, aQ[k] - aP[k], aP[k]);
+    return cv;
+  };
+  int  count = 0;
+  CV   pv[2][3];
+  if(nIn == 2)
+  {
+    const int k = firstOut, a = (k + 1) % 3, b = (k + 2) % 3;
+    const CV  A = cut(a, k), B = cut(b, k), va = original(a), vb = original(b);
+    pv[0][0] = A;
+    pv[0][1] = va;
+    pv[0][2] = vb;
+    pv[1][0] = A;
+    pv[1][1] = vb;
+    pv[1][2] = B;
+    count    = 2;
+  }
+  else
+  {
+    const int a = firstIn, b = (a + 1) % 3, cc = (a + 2) % 3;
+    pv[0][0] = original(a);
+    pv[0][1] = cut(a, b);
+    pv[0][2] = cut(a, cc);
+    count    = 1;
+  }
+  for(int s = 0; s < count; s++)
+    for(int k = 0; k < 3; k++)
+    {
+      if(!pv[s][k].v.valid)
+        return 0;
+      out[s].v[k] = pv[s][k].v;
+      memcpy(out[s].attr[k], pv[s][k].attr, sizeof(pv[s][k].attr));
+    }
+  return count;
+}
+
 inline int64_t edgeFn(const Tri& t, int k, int64_t px, int64_t py)
 {
   const int a = (k + 1) % 3, b = (k + 2) % 3;
@@ -780,12 +886,29 @@ void drawRange(OracleCtx* c, uint32_t firstIndex, uint32_t indexCount, int mode)
     const int    rows0 = (int)((uint64_t)c->H * tid / nt), rows1 = (int)((uint64_t)c->H * (tid + 1) / nt);
     ThreadStats& st = sts[tid];
     Tri          t;
+    ClipPiece    pieces[2];
     for(uint32_t i = 0; i + 2 < indexCount; i += 3)
     {
       const uint32_t* ix = &c->idx[firstIndex + i];
-      if(!setupTri(c, ix[0], ix[1], ix[2], mode == 0, t, st))
+      const TVert* const v[3] = {&c->tv[ix[0]], &c->tv[ix[1]], &c->tv[ix[2]]};
+      if(v[0]->valid && v[1]->valid && v[2]->valid)
+      {
+        const float* const attr[3] = {&c->verts[(size_t)ix[0] * 10], &c->verts[(size_t)ix[1] * 10], &c->verts[(size_t)ix[2] * 10]};
+        if(setupTriFrom(v, attr, mode == 0, t))
+          rasterTri(c, t, mode, rows0, rows1, st);
         continue;
-      rasterTri(c, t, mode, rows0, rows1, st);
+      }
+      /* a vertex has no post-projection position: behind the near plane => clip; anything else => rejected */
+      const int n = clipTriangleNear(c, ix, pieces);
+      if(n == 0 && mode != 1)  /* counted once per draw: Loop32's depth pre-pass walks the same triangles again */
+        st.rejected++;
+      for(int s = 0; s < n; s++)
+      {
+        const TVert* const pvv[3]  = {&pieces[s].v[0], &pieces[s].v[1], &pieces[s].v[2]};
+        const float* const pat[3] = {pieces[s].attr[0], pieces[s].attr[1], pieces[s].attr[2]};
+        if(setupTriFrom(pvv, pat, mode == 0, t))
+          rasterTri(c, t, mode, rows0, rows1, st);
+      }
     }
   }
   for(int i = 0; i < nt; i++)

@@ -64,7 +64,7 @@ typedef struct OracleStats
   uint64_t fragmentsTail;    /* invocations that emitted a non-zero ROP colour */
   uint64_t opaqueFragments;
   uint64_t trianglesDrawn;   /* transparent triangles submitted */
-  uint64_t trianglesRejected;/* w<=0 or out of guard band */
+  uint64_t trianglesRejected;/* entirely behind the near plane, or not representable (far plane, guard band) */
   uint64_t llCounter;        /* final value of the linked-list counter */
 } OracleStats;
 

@@ -168,14 +168,17 @@ void freeBins(BinBuffers& b)
   cudaFree(b.pairVal[1]);
   cudaFree(b.tileStart);
   cudaFree(b.pairInfo);
+  cudaFree(b.clipEntries);
   cudaFree(b.scratch);
   cudaFree(b.tileOrder);
   b = BinBuffers{};
 }
 
 // (re)allocates the binning buffers of one draw for `triCount` triangles and `pairCapacity` pairs
-int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
+int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity, size_t clipCapacity = 0)
 {
+  // pieces of near-clipped triangles (oit_clip.cuh): rare, so the table starts small and grows like the pair buffers
+  clipCapacity = std::max<size_t>(std::max<size_t>(clipCapacity, b.clipCapacity), 4096);
   const size_t numTiles = (size_t)c->fp.tilesX * c->fp.tileRowsLocal;
   freeBins(b);
   b.pairCapacity = pairCapacity;
@@ -188,8 +191,10 @@ int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity)
     CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
   }
   CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 2 * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 2 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 4 * sizeof(uint32_t)));
+  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 4 * sizeof(uint32_t)));
+  b.clipCapacity = clipCapacity;
+  CUDA_TRY(c, cudaMalloc(&b.clipEntries, clipCapacity * sizeof(ClipEntry)));
   CUDA_TRY(c, cudaMalloc(&b.tileOrder, std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
   CUDA_TRY(c, cudaMalloc(&b.scratch, b.scratchWords * sizeof(uint32_t)));
   c->graphValid = false;  // the captured frame refers to the old buffers
@@ -247,6 +252,8 @@ int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullB
   c->drawTris[which]      = triCount;
   if(triCount == 0)
     return OIT_OK;
+  c->fp.clipEntries  = b.clipEntries;  // k_bin_emit fills the draw's clip table
+  c->fp.clipCapacity = (uint32_t)b.clipCapacity;
   c->launches += launchBin(c->fp, b, firstTri, triCount, cullBack, &c->sortedBuf[which], c->stream);
   return OIT_OK;
 }
@@ -267,16 +274,18 @@ int growBinsIfNeeded(OitCtx* c, bool* grown)
     BinBuffers& b = c->bins[which];
     if(!b.pairInfo || c->drawTris[which] == 0)
       continue;
-    uint32_t info[2] = {0, 0};
+    uint32_t info[4] = {0, 0, 0, 0};  // pairs present, pairs wanted, clip entries wanted
     if(mirrored)
-      memcpy(info, c->hostMirror + NUM_STAT_SLOTS + which, sizeof(info));
+      memcpy(info, c->hostMirror + NUM_STAT_SLOTS + 2 * which, sizeof(info));
     else
       CUDA_TRY(c, cudaMemcpy(info, b.pairInfo, sizeof(info), cudaMemcpyDeviceToHost));
     c->pairTotal[which] = info[1];
-    if(overflow && info[1] > b.pairCapacity)
+    if(overflow && (info[1] > b.pairCapacity || info[2] > b.clipCapacity))
     {
-      const size_t tris = b.triCapacity;
-      const int    r    = allocBins(c, b, tris, (size_t)info[1] + info[1] / 4 + 1024);
+      const size_t tris  = b.triCapacity;
+      const size_t pairs = info[1] > b.pairCapacity ? (size_t)info[1] + info[1] / 4 + 1024 : b.pairCapacity;
+      const size_t clips = info[2] > b.clipCapacity ? (size_t)info[2] + info[2] / 4 + 1024 : b.clipCapacity;
+      const int    r     = allocBins(c, b, tris, pairs, clips);
       if(r != OIT_OK)
         return r;
       *grown = true;
@@ -290,6 +299,8 @@ void useBins(OitCtx* c, int which)
   c->fp.pairTri   = c->bins[which].pairVal[c->sortedBuf[which]];
   c->fp.tileStart = c->bins[which].tileStart;
   c->fp.tileOrder = c->bins[which].tileOrder;
+  c->fp.clipEntries  = c->bins[which].clipEntries;
+  c->fp.clipCapacity = (uint32_t)c->bins[which].clipCapacity;
 }
 
 int ensureSceneBins(OitCtx* c)
@@ -429,8 +440,8 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   for(int i = 0; i < UBO_RING; i++)
     CREATE_CUDA(cudaEventCreateWithFlags(&c->uboEv[i], cudaEventDisableTiming));
   c->asyncRender = getenv("OIT_B200_SYNC_RENDER") == nullptr;
-  CREATE_CUDA(cudaMallocHost(&c->hostMirror, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long)));
-  memset(c->hostMirror, 0, (NUM_STAT_SLOTS + 2) * sizeof(unsigned long long));
+  CREATE_CUDA(cudaMallocHost(&c->hostMirror, (NUM_STAT_SLOTS + 4) * sizeof(unsigned long long)));
+  memset(c->hostMirror, 0, (NUM_STAT_SLOTS + 4) * sizeof(unsigned long long));
   memset(c->hostUbo, 0, UBO_RING * sizeof(DeviceUbo));
   c->useGraph = getenv("OIT_B200_NO_GRAPH") == nullptr;
 
@@ -993,7 +1004,7 @@ static int issueFrame(OitCtx* c)
   CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror, c->stats.p, NUM_STAT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   for(int which = 0; which < 2; which++)
     if(c->bins[which].pairInfo && c->drawTris[which] > 0)
-      CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror + NUM_STAT_SLOTS + which, c->bins[which].pairInfo, 2 * sizeof(uint32_t),
+      CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror + NUM_STAT_SLOTS + 2 * which, c->bins[which].pairInfo, 4 * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, c->stream));
   return OIT_OK;
 }

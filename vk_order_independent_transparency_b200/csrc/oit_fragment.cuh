@@ -62,33 +62,14 @@ __device__ __forceinline__ float depthAt(const TriSlot& s, const Bary& b)
   return clamp01(__fmaf_rn(b.l2, s.dz2, __fmaf_rn(b.l1, s.dz1, s.z0)));
 }
 
-// Interpolants (shaderCommon.glsl:25-31) perspective-correct at `b`, then shading() (shaderCommon.glsl:36-56)
-template <bool NEED_VIEWZ>
-__device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s, const Bary& b, float& viewz)
+// TriSlot::box flags of a piece of a near-clipped triangle: vidx[0] is the index of its ClipEntry (the frame's clip table,
+// oit_clip.cuh / k_bin_emit), the geometry (x, y, z, iw) is the piece's
+constexpr uint32_t SLOT_CLIPPED = 1u << 21;  // the slot is a piece of a near-clipped triangle
+constexpr uint32_t SLOT_SWAPPED = 1u << 23;  // its vertices 1 and 2 were exchanged to make area2 > 0
+
+// shading() + goochLighting() (shaderCommon.glsl:36-56) of the interpolated normal (v[0..2]) and colour (v[3..6])
+__device__ __forceinline__ Color4 shadeVaryings(const DeviceUbo* ubo, const float v[7])
 {
-  const float q0 = __fmul_rn(b.l0, s.iw[0]), q1 = __fmul_rn(b.l1, s.iw[1]), q2 = __fmul_rn(b.l2, s.iw[2]);
-  const float rden = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(q0, q1), q2));
-  const float* a0 = p.verts + (size_t)s.vidx[0] * 10;
-  const float* a1 = p.verts + (size_t)s.vidx[1] * 10;
-  const float* a2 = p.verts + (size_t)s.vidx[2] * 10;
-  // normal (3 floats at byte 12) + colour (4 floats at byte 24) of each vertex: one 32-bit and three 64-bit loads
-  float v0[7], v1[7], v2[7];
-  auto  fetch = [](const float* a, float* o) {
-    o[0]            = __ldg(a + 3);
-    const float2 n  = __ldg(reinterpret_cast<const float2*>(a + 4));
-    const float2 c0 = __ldg(reinterpret_cast<const float2*>(a + 6));
-    const float2 c1 = __ldg(reinterpret_cast<const float2*>(a + 8));
-    o[1] = n.x; o[2] = n.y; o[3] = c0.x; o[4] = c0.y; o[5] = c1.x; o[6] = c1.y;
-  };
-  fetch(a0, v0);
-  fetch(a1, v1);
-  fetch(a2, v2);
-  float v[7];
-#pragma unroll
-  for(int k = 0; k < 7; k++)
-    v[k] = __fmul_rn(__fmaf_rn(q2, v2[k], __fmaf_rn(q1, v1[k], __fmul_rn(q0, v0[k]))), rden);
-  if(NEED_VIEWZ)
-    viewz = __fmul_rn(__fmaf_rn(q2, p.tv[s.vidx[2]].viewz, __fmaf_rn(q1, p.tv[s.vidx[1]].viewz, __fmul_rn(q0, p.tv[s.vidx[0]].viewz))), rden);
   const float LX = -0.40824829046386301637f, LY = 0.81649658092772603273f, LZ = 0.40824829046386301637f;
   const float len2 = __fmaf_rn(v[2], v[2], __fmaf_rn(v[1], v[1], __fmul_rn(v[0], v[0])));
   float       nx = 0.f, ny = 0.f, nz = 0.f;
@@ -106,8 +87,50 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
   c.r = __fmul_rn(v[3], __fmaf_rn(0.0f, om, warmth));
   c.g = __fmul_rn(v[4], __fmaf_rn(0.25f, om, warmth));
   c.b = __fmul_rn(v[5], __fmaf_rn(0.75f, om, warmth));
-  c.a = clamp01(__fmaf_rn(v[6], p.ubo->alphaWidth, p.ubo->alphaMin));
+  c.a = clamp01(__fmaf_rn(v[6], ubo->alphaWidth, ubo->alphaMin));
   return c;
+}
+
+// Interpolants (shaderCommon.glsl:25-31) perspective-correct at `b`, then shading() (shaderCommon.glsl:36-56)
+template <bool NEED_VIEWZ>
+__device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s, const Bary& b, float& viewz)
+{
+  const float q0 = __fmul_rn(b.l0, s.iw[0]), q1 = __fmul_rn(b.l1, s.iw[1]), q2 = __fmul_rn(b.l2, s.iw[2]);
+  const float rden = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(q0, q1), q2));
+  // a piece of a near-clipped triangle reads its three vertex records (and view depths) from its ClipEntry; slot vertex
+  // k is piece vertex k, or 3 - k for k > 0 when the set-up exchanged vertices 1 and 2
+  const bool       clipped = (s.box & SLOT_CLIPPED) != 0;
+  const ClipEntry* ce      = p.clipEntries + s.vidx[0];
+  const int        m1      = (s.box & SLOT_SWAPPED) ? 2 : 1;
+  const float*     a0      = clipped ? ce->attr[0] : p.verts + (size_t)s.vidx[0] * 10;
+  const float*     a1      = clipped ? ce->attr[m1] : p.verts + (size_t)s.vidx[1] * 10;
+  const float*     a2      = clipped ? ce->attr[3 - m1] : p.verts + (size_t)s.vidx[2] * 10;
+  // normal (3 floats at byte 12) + colour (4 floats at byte 24) of each vertex: one 32-bit and three 64-bit loads
+  float v0[7], v1[7], v2[7];
+  auto  fetch = [](const float* a, float* o) {
+    o[0]            = __ldg(a + 3);
+    const float2 n  = __ldg(reinterpret_cast<const float2*>(a + 4));
+    const float2 c0 = __ldg(reinterpret_cast<const float2*>(a + 6));
+    const float2 c1 = __ldg(reinterpret_cast<const float2*>(a + 8));
+    o[1] = n.x; o[2] = n.y; o[3] = c0.x; o[4] = c0.y; o[5] = c1.x; o[6] = c1.y;
+  };
+  fetch(a0, v0);
+  fetch(a1, v1);
+  fetch(a2, v2);
+  float vz0 = 0.f, vz1 = 0.f, vz2 = 0.f;
+  if(NEED_VIEWZ)
+  {
+    vz0 = clipped ? ce->v[0].viewz : p.tv[s.vidx[0]].viewz;
+    vz1 = clipped ? ce->v[m1].viewz : p.tv[s.vidx[1]].viewz;
+    vz2 = clipped ? ce->v[3 - m1].viewz : p.tv[s.vidx[2]].viewz;
+  }
+  float v[7];
+#pragma unroll
+  for(int k = 0; k < 7; k++)
+    v[k] = __fmul_rn(__fmaf_rn(q2, v2[k], __fmaf_rn(q1, v1[k], __fmul_rn(q0, v0[k]))), rden);
+  if(NEED_VIEWZ)
+    viewz = __fmul_rn(__fmaf_rn(q2, vz2, __fmaf_rn(q1, vz1, __fmul_rn(q0, vz0))), rden);
+  return shadeVaryings(p.ubo, v);
 }
 
 // ---- fragment programs ----------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 // Everything here is asynchronous: the number of (tile, triangle) pairs stays on the device (the sort and the range
 // kernels read it from memory, grids are sized for the buffer capacity), so a whole frame can be replayed as one CUDA
 // graph.  If the pair buffer is too small an overflow flag is raised and the host grows it and renders again.
+#include "oit_clip.cuh"
 #include "oit_device.cuh"
 
 namespace oit {
@@ -27,25 +28,8 @@ __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
 #pragma unroll
     for(int r = 0; r < 4; r++)
       clip[r] = __fmaf_rn(M[0 + r], px, __fmaf_rn(M[4 + r], py, __fmaf_rn(M[8 + r], pz, M[12 + r])));
-    TVert t;
-    t.viewz = __fmaf_rn(V[2], px, __fmaf_rn(V[6], py, __fmaf_rn(V[10], pz, V[14])));
-    t.x     = INT32_MIN;
-    t.y     = 0;
-    t.z     = 0.f;
-    t.invw  = 0.f;
-    if(clip[3] > 0.f && clip[3] < __int_as_float(0x7f800000))
-    {
-      const float invw = __fdiv_rn(1.0f, clip[3]);
-      const float nx = __fmul_rn(clip[0], invw), ny = __fmul_rn(clip[1], invw), nz = __fmul_rn(clip[2], invw);
-      const float xs = __fmaf_rn(nx, hw, hw), ys = __fmaf_rn(ny, hh, hh);
-      if(fabsf(xs) < GUARD_BAND_PX && fabsf(ys) < GUARD_BAND_PX && nz >= 0.f && nz <= 1.f)
-      {
-        t.x    = __float2int_rn(__fmul_rn(xs, 256.0f));
-        t.y    = __float2int_rn(__fmul_rn(ys, 256.0f));
-        t.z    = nz;
-        t.invw = invw;
-      }
-    }
+    const float viewz = __fmaf_rn(V[2], px, __fmaf_rn(V[6], py, __fmaf_rn(V[10], pz, V[14])));
+    const TVert t     = finishVertex(clip, viewz, hw, hh);
     p.tv[i] = t;
   }
 }
@@ -121,21 +105,26 @@ struct TileRange
 };
 
 // The pixel range that can contain a covered sample: a sample of pixel px lies at px*256 + off, off in [lo, hi].
-__device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri, bool cullBack, TileRange& r, bool& rejected)
+// what the tile-range / band logic reads, BY VALUE for the out-of-line clipped path (see ClipInput)
+struct BinView
 {
-  const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
-  const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
-  rejected         = a.x == INT32_MIN || b.x == INT32_MIN || c.x == INT32_MIN;
-  if(rejected)
-    return false;
+  ClipInput in;
+  int       msaa, stripTileRows, bandCount, bandIndex, tilesX;
+};
+__device__ __forceinline__ BinView binView(const FrameParams& p)
+{
+  return BinView{clipInput(p), p.msaa, p.stripTileRows, p.bandCount, p.bandIndex, p.tilesX};
+}
+__device__ __forceinline__ bool tvTileRange(const BinView& v, const TVert& a, const TVert& b, const TVert& c, bool cullBack, TileRange& r)
+{
   const long long area2 = (long long)(b.x - a.x) * (c.y - a.y) - (long long)(c.x - a.x) * (b.y - a.y);
   if(area2 == 0 || (cullBack && area2 > 0))
     return false;
-  const int lo = p.msaa == 1 ? 128 : (p.msaa == 4 ? 32 : 16), hi = 256 - lo;
+  const int lo = v.msaa == 1 ? 128 : (v.msaa == 4 ? 32 : 16), hi = 256 - lo;
   const int minx = min(a.x, min(b.x, c.x)), maxx = max(a.x, max(b.x, c.x));
   const int miny = min(a.y, min(b.y, c.y)), maxy = max(a.y, max(b.y, c.y));
-  const int px0 = max((minx - hi + 255) >> 8, 0), px1 = min((maxx - lo) >> 8, p.W - 1);
-  const int py0 = max((miny - hi + 255) >> 8, 0), py1 = min((maxy - lo) >> 8, p.H - 1);
+  const int px0 = max((minx - hi + 255) >> 8, 0), px1 = min((maxx - lo) >> 8, v.in.W - 1);
+  const int py0 = max((miny - hi + 255) >> 8, 0), py1 = min((maxy - lo) >> 8, v.in.H - 1);
   if(px0 > px1 || py0 > py1)
     return false;
   r.tx0 = px0 >> TILE_SHIFT;
@@ -144,24 +133,108 @@ __device__ __forceinline__ bool triTileRange(const FrameParams& p, uint32_t tri,
   r.ty1 = py1 >> TILE_SHIFT;
   return true;
 }
-
-__global__ void __launch_bounds__(256) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
-                                                   uint32_t* __restrict__ counts)
+__device__ __forceinline__ uint32_t ownedTiles(const BinView& v, const TileRange& r)
 {
-  unsigned long long nRejected = 0;
-  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+  uint32_t  n  = 0;
+  const int nx = r.tx1 - r.tx0 + 1;
+  for(int R = r.ty0; R <= r.ty1; R++)
+    if(tileRowOwner(R, v.stripTileRows, v.bandCount) == v.bandIndex)
+      n += nx;
+  return n;
+}
+__device__ __forceinline__ uint32_t emitTiles(const BinView& v, const TileRange& r, uint32_t val, uint32_t o, uint32_t* __restrict__ keys,
+                                              uint32_t* __restrict__ vals)
+{
+  for(int R = r.ty0; R <= r.ty1; R++)
+    if(tileRowOwner(R, v.stripTileRows, v.bandCount) == v.bandIndex)
+    {
+      const uint32_t rowKey = (uint32_t)tileRowToLocal(R, v.stripTileRows, v.bandCount) * v.tilesX;
+      for(int tx = r.tx0; tx <= r.tx1; tx++, o++)
+      {
+        keys[o] = rowKey + tx;
+        vals[o] = val;  // emitted in primitive order; the stable sort keeps it (and the pieces of a primitive) per tile
+      }
+    }
+  return o;
+}
+
+// A triangle with a vertex that has no post-projection position (oit_clip.cuh): the pairs of its pieces.  Out of line:
+// rare, and the clipper's state stays out of the binning kernels' fast path.  Returns the pair count; *rejected = no piece.
+static __device__ __noinline__ uint32_t countClipped(const BinView v, uint32_t i0, uint32_t i1, uint32_t i2, bool cullBack, bool* rejected)
+{
+  const ClipResult cr = clipTriangleNear(v.in, i0, i1, i2);
+  *rejected           = cr.count == 0;
+  uint32_t n          = 0;
+  for(int s = 0; s < cr.count; s++)
   {
     TileRange r;
-    uint32_t  n = 0;
-    bool      rejected;
-    if(triTileRange(p, firstTri + t, cullBack != 0, r, rejected))
+    if(tvTileRange(v, cr.v[s][0].v, cr.v[s][1].v, cr.v[s][2].v, cullBack, r))
+      n += ownedTiles(v, r);
+  }
+  return n;
+}
+// ... and their emission: every piece that owns tiles gets a ClipEntry (vertices + vertex records), its pairs carry the
+// entry's index instead of the triangle's
+static __device__ __noinline__ void emitClipped(const BinView v, uint32_t i0, uint32_t i1, uint32_t i2, bool cullBack, uint32_t o,
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, ClipEntry* __restrict__ entries,
+                                                uint32_t clipCapacity, uint32_t* __restrict__ clipCount, unsigned long long* __restrict__ overflow)
+{
+  const ClipResult cr    = clipTriangleNear(v.in, i0, i1, i2);
+  const uint32_t   ix[3] = {i0, i1, i2};
+  for(int s = 0; s < cr.count; s++)
+  {
+    TileRange r;
+    if(!tvTileRange(v, cr.v[s][0].v, cr.v[s][1].v, cr.v[s][2].v, cullBack, r) || ownedTiles(v, r) == 0u)
+      continue;
+    const uint32_t e   = atomicAdd(clipCount, 1u);
+    uint32_t       val = PAIR_SKIP;
+    if(e < clipCapacity)
     {
-      const int nx = r.tx1 - r.tx0 + 1;
-      for(int R = r.ty0; R <= r.ty1; R++)
-        if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
-          n += nx;
+      ClipEntry& ce = entries[e];
+      for(int m = 0; m < 3; m++)
+      {
+        const ClipVert& cv = cr.v[s][m];
+        ce.v[m]            = cv.v;
+        const float* aP    = v.in.verts + (size_t)ix[cv.i] * 10;
+        const float* aQ    = v.in.verts + (size_t)ix[cv.j] * 10;
+        for(int c = 0; c < 10; c++)
+          ce.attr[m][c] = cv.i == cv.j ? aP[c] : __fmaf_rn(cv.t, __fsub_rn(aQ[c], aP[c]), aP[c]);
+      }
+      ce.pad0   = 0u;
+      ce.pad[0] = ce.pad[1] = 0u;
+      val                   = PAIR_CLIPPED | e;
     }
-    nRejected += rejected ? 1u : 0u;
+    else
+      atomicAdd(overflow, 1ull);  // the host grows the table and renders the frame again
+    o = emitTiles(v, r, val, o, keys, vals);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
+                                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ pairInfo)
+{
+  unsigned long long nRejected = 0;
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    pairInfo[2] = 0u;  // clip entries handed out by k_bin_emit (which runs after this kernel)
+  const BinView v = binView(p);
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+  {
+    const uint32_t tri = firstTri + t;
+    const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
+    const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
+    uint32_t       n = 0;
+    if(a.x != INT32_MIN && b.x != INT32_MIN && c.x != INT32_MIN)
+    {
+      TileRange r;
+      if(tvTileRange(v, a, b, c, cullBack != 0, r))
+        n = ownedTiles(v, r);
+    }
+    else
+    {
+      bool rejected;
+      n = countClipped(v, i0, i1, i2, cullBack != 0, &rejected);
+      nRejected += rejected ? 1u : 0u;
+    }
     counts[t] = n;
   }
   if(nRejected)
@@ -182,25 +255,23 @@ __global__ void __launch_bounds__(256) k_bin_emit(const FrameParams p, uint32_t 
     if(total > capacity)
       atomicAdd(&p.stats[STAT_OVERFLOW], 1ull);
   }
+  const BinView v = binView(p);
   for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
   {
     const uint32_t o0 = offsets[t], o1 = offsets[t + 1];
     if(o0 == o1 || o1 > capacity)
       continue;
-    TileRange r;
-    bool      rejected;
-    triTileRange(p, firstTri + t, cullBack != 0, r, rejected);
-    uint32_t o = o0;
-    for(int R = r.ty0; R <= r.ty1; R++)
-      if(tileRowOwner(R, p.stripTileRows, p.bandCount) == p.bandIndex)
-      {
-        const uint32_t rowKey = (uint32_t)tileRowToLocal(R, p.stripTileRows, p.bandCount) * p.tilesX;
-        for(int tx = r.tx0; tx <= r.tx1; tx++, o++)
-        {
-          keys[o] = rowKey + tx;
-          vals[o] = firstTri + t;
-        }
-      }
+    const uint32_t tri = firstTri + t;
+    const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
+    const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
+    if(a.x != INT32_MIN && b.x != INT32_MIN && c.x != INT32_MIN)
+    {
+      TileRange r;
+      if(tvTileRange(v, a, b, c, cullBack != 0, r))
+        emitTiles(v, r, tri, o0, keys, vals);
+    }
+    else
+      emitClipped(v, i0, i1, i2, cullBack != 0, o0, keys, vals, p.clipEntries, p.clipCapacity, pairInfo + 2, p.stats + STAT_OVERFLOW);
   }
 }
 
@@ -439,7 +510,7 @@ int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint
     return 0;
   }
   const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
-  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts);
+  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairInfo);
   launches += 1 + launchScan(b.counts, b.counts, triCount, b.scratch, s);
   k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairKey[0], b.pairVal[0],
                                     (uint32_t)b.pairCapacity, b.pairInfo);

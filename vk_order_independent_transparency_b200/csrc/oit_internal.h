@@ -1,6 +1,7 @@
 // oit_internal.h -- structures shared by the host API and the CUDA translation units of liboit_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include <string>
@@ -46,6 +47,21 @@ struct TVert
   float   viewz;  // (viewMatrix * pos).z  (Interpolants.depth)
 };
 static_assert(sizeof(TVert) == 20, "TVert layout");
+
+// One piece of a near-clipped triangle (oit_clip.cuh), written by the binning of the frame and read by the raster kernel:
+// the piece's post-projection vertices and, per vertex, where its attributes come from.
+struct ClipEntry
+{
+  TVert    v[3];      // post-projection vertices of the piece
+  uint32_t pad0;      // (keeps the records 8-byte aligned for the 64-bit attribute loads)
+  float    attr[3][10];  // their vertex records (pos3 unused, normal3, colour4): an original vertex's, or the clip-space
+                      // interpolation fma(t, attr[Q] - attr[P], attr[P]) along the cut edge -- same layout as the scene's
+                      // vertex buffer, so that the shading reads either through the same code
+  uint32_t pad[2];
+};
+static_assert(sizeof(ClipEntry) == 192 && offsetof(ClipEntry, attr) % 8 == 0, "ClipEntry layout");
+constexpr uint32_t PAIR_CLIPPED = 0x80000000u;  // pair value: bit 31 set = index of a ClipEntry instead of a triangle
+constexpr uint32_t PAIR_SKIP    = 0xFFFFFFFFu;  // a piece that found no room in the entry table (the frame is rendered again)
 
 enum StatSlot
 {
@@ -122,6 +138,8 @@ struct FrameParams
   const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order
   const uint32_t* tileStart;  // [numLocalTiles + 1]
   const uint32_t* tileOrder;  // [numLocalTiles] tile handled by CTA i: heaviest triangle lists first
+  ClipEntry*      clipEntries;  // pieces of the near-clipped triangles of the current draw
+  uint32_t        clipCapacity;
 };
 
 // Fused frame kernel, k-buffer techniques without sample shading: the tile's A-buffer slice and aux words can live in
@@ -167,6 +185,8 @@ struct BinBuffers
   uint32_t* tileStart;   // [numLocalTiles + 1]
   uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics)
   uint32_t* tileOrder;   // [numLocalTiles] launch order of the tiles: heaviest lists first
+  ClipEntry* clipEntries;  // [clipCapacity]; pairInfo[2] = entries wanted by the last frame
+  size_t     clipCapacity;
   uint32_t* scratch;     // scan / histogram scratch
   size_t    scratchWords;
   size_t    pairCapacity;

@@ -267,6 +267,64 @@ __device__ __forceinline__ void processFragment(FragCtx& ctx, const TriSlot& s, 
 #ifndef OIT_MIN_BLOCKS
 #define OIT_MIN_BLOCKS 5
 #endif
+// Triangle set-up of one tile-list entry: orientation (area2 > 0), depth plane, fill-rule bias bits, the box of tile pixels
+// that can hold a covered sample.  Returns the number of (triangle, pixel) items, padded to ITEMS_PER_THREAD.
+// lo: smallest sample offset of the sample pattern in 1/256 px (samples sit in [lo, 256 - lo]).
+__device__ __forceinline__ uint32_t setupSlot(TVert v0, TVert v1, TVert v2, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t clipBits, int W, int H,
+                                              int tileX0, int tileY0, int lo, TriSlot& s)
+{
+  const int hi    = 256 - lo;
+  long long area2 = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
+  if(area2 < 0)
+  {
+    const TVert tv = v1;
+    v1             = v2;
+    v2             = tv;
+    if(clipBits == 0u)
+    {
+      const uint32_t ti = i1;
+      i1                = i2;
+      i2                = ti;
+    }
+    else
+      clipBits |= SLOT_SWAPPED;  // vidx[0] stays the clip entry: shadeAt replays the exchange
+    area2 = -area2;
+  }
+  const int minx = min(v0.x, min(v1.x, v2.x)), maxx = max(v0.x, max(v1.x, v2.x));
+  const int miny = min(v0.y, min(v1.y, v2.y)), maxy = max(v0.y, max(v1.y, v2.y));
+  const int px0 = max((minx - hi + 255) >> 8, tileX0), px1 = min((maxx - lo) >> 8, min(tileX0 + TILE_W, W) - 1);
+  const int py0 = max((miny - hi + 255) >> 8, tileY0), py1 = min((maxy - lo) >> 8, min(tileY0 + TILE_H, H) - 1);
+  // fill-rule bias of edge k (opposite vertex k, from vertex k+1 to vertex k+2): Vulkan / D3D top-left rule, y down, area2 > 0
+  auto notTopLeft = [](int dx, int dy) { return ((dy == 0 && dx > 0) || dy < 0) ? 0u : 1u; };
+  const uint32_t biasBits = notTopLeft(v2.x - v1.x, v2.y - v1.y) | (notTopLeft(v0.x - v2.x, v0.y - v2.y) << 1) | (notTopLeft(v1.x - v0.x, v1.y - v0.y) << 2);
+  const bool     zSafe    = fmaxf(v0.z, fmaxf(v1.z, v2.z)) < 0.9999f;
+  // extent <= 2^14 sub-pixels: |delta| <= 2^14, |sample - vertex| <= 2^14 + 2^12 inside the clipped box, so every
+  // edge function and area fits comfortably in int32
+  const bool small  = (maxx - minx) <= 16384 && (maxy - miny) <= 16384;
+  uint32_t   box = 0, rcpW = 0, nItems = 0;
+  if(px0 <= px1 && py0 <= py1)
+  {
+    const int bw = px1 - px0 + 1, bh = py1 - py0 + 1;
+    // padded to a multiple of ITEMS_PER_THREAD so that the items of one thread always belong to one triangle
+    nItems = (uint32_t)(bw * bh + ITEMS_PER_THREAD - 1) & ~(uint32_t)(ITEMS_PER_THREAD - 1);
+    box    = (uint32_t)(px0 - tileX0) | ((uint32_t)(py0 - tileY0) << 4) | ((uint32_t)(bw - 1) << 8) | ((uint32_t)(bh - 1) << 12)
+          | (biasBits << 16) | ((zSafe ? 1u : 0u) << 19) | ((small ? 1u : 0u) << 20) | clipBits;
+    rcpW = (65535u + bw) / bw;
+  }
+  // s is the slot in shared memory: every field is written exactly once, from registers
+  s.x[0] = v0.x; s.x[1] = v1.x; s.x[2] = v2.x;
+  s.y[0] = v0.y; s.y[1] = v1.y; s.y[2] = v2.y;
+  s.z0   = v0.z;
+  s.dz1  = __fsub_rn(v1.z, v0.z);
+  s.dz2  = __fsub_rn(v2.z, v0.z);
+  s.iw[0] = v0.invw; s.iw[1] = v1.invw; s.iw[2] = v2.invw;
+  s.vidx[0] = i0; s.vidx[1] = i1; s.vidx[2] = i2;
+  s.rarea = __fdiv_rn(1.0f, __ll2float_rn(area2));
+  s.box   = box;
+  s.rcpW  = rcpW;
+  return nItems;
+}
+
 // the technique a colour pass belongs to (the fused composite is specialised on it)
 __host__ __device__ constexpr int passAlgorithm(int pass)
 {
@@ -375,7 +433,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
     }
   }
   uint32_t parity = 0;
-  const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16), hi = 256 - lo;
+  const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16);  // samples sit in [lo, 256 - lo] of the pixel
   __syncthreads();
 
   for(uint32_t base = listBegin; base < listEnd; base += RASTER_THREADS)
@@ -384,58 +442,24 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_MIN_BLOCKS) k_raster(const
     uint32_t nItems = 0;
     if(base + tid < listEnd)
     {
-      const uint32_t tri = p.pairTri[base + tid];
-      uint32_t       ix[3] = {p.indices[3 * (size_t)tri], p.indices[3 * (size_t)tri + 1], p.indices[3 * (size_t)tri + 2]};
-      TVert          v0 = p.tv[ix[0]], v1 = p.tv[ix[1]], v2 = p.tv[ix[2]];
-      long long      area2 = (long long)(v1.x - v0.x) * (v2.y - v0.y) - (long long)(v2.x - v0.x) * (v1.y - v0.y);
-      if(area2 < 0)
+      const uint32_t val = p.pairTri[base + tid];
+      if(!(val & PAIR_CLIPPED))
       {
-        const TVert tv = v1;
-        v1             = v2;
-        v2             = tv;
-        const uint32_t ti = ix[1];
-        ix[1]             = ix[2];
-        ix[2]             = ti;
-        area2             = -area2;
+        const uint32_t i0 = p.indices[3 * (size_t)val], i1 = p.indices[3 * (size_t)val + 1], i2 = p.indices[3 * (size_t)val + 2];
+        nItems            = setupSlot(p.tv[i0], p.tv[i1], p.tv[i2], i0, i1, i2, 0u, p.W, p.H, tileX0, tileY0, lo, slots[tid]);
       }
-      TriSlot s;
-      s.x[0] = v0.x; s.x[1] = v1.x; s.x[2] = v2.x;
-      s.y[0] = v0.y; s.y[1] = v1.y; s.y[2] = v2.y;
-      s.z0   = v0.z;
-      s.dz1  = __fsub_rn(v1.z, v0.z);
-      s.dz2  = __fsub_rn(v2.z, v0.z);
-      s.iw[0] = v0.invw; s.iw[1] = v1.invw; s.iw[2] = v2.invw;
-      s.vidx[0] = ix[0]; s.vidx[1] = ix[1]; s.vidx[2] = ix[2];
-      s.rarea = __fdiv_rn(1.0f, __ll2float_rn(area2));
-      const int minx = min(v0.x, min(v1.x, v2.x)), maxx = max(v0.x, max(v1.x, v2.x));
-      const int miny = min(v0.y, min(v1.y, v2.y)), maxy = max(v0.y, max(v1.y, v2.y));
-      const int px0 = max((minx - hi + 255) >> 8, tileX0), px1 = min((maxx - lo) >> 8, min(tileX0 + TILE_W, p.W) - 1);
-      const int py0 = max((miny - hi + 255) >> 8, tileY0), py1 = min((maxy - lo) >> 8, min(tileY0 + TILE_H, p.H) - 1);
-      uint32_t  biasBits = 0;
-#pragma unroll
-      for(int k = 0; k < 3; k++)
+      else if(val != PAIR_SKIP)
       {
-        const int a = (k + 1) % 3, b = (k + 2) % 3;
-        const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
-        const bool topLeft = (dy == 0 && dx > 0) || dy < 0;  // Vulkan / D3D top-left rule, y down, area2 > 0
-        biasBits |= (topLeft ? 0u : 1u) << k;
+        // a piece of a near-clipped triangle: its vertices come from the frame's clip table (oit_clip.cuh, k_bin_emit)
+        const uint32_t   e  = val & ~PAIR_CLIPPED;
+        const ClipEntry& ce = p.clipEntries[e];
+        nItems              = setupSlot(ce.v[0], ce.v[1], ce.v[2], e, 0u, 0u, SLOT_CLIPPED, p.W, p.H, tileX0, tileY0, lo, slots[tid]);
       }
-      const bool zSafe = fmaxf(v0.z, fmaxf(v1.z, v2.z)) < 0.9999f;
-      // extent <= 2^14 sub-pixels: |delta| <= 2^14, |sample - vertex| <= 2^14 + 2^12 inside the clipped box, so every
-      // edge function and area fits comfortably in int32
-      const bool small = (maxx - minx) <= 16384 && (maxy - miny) <= 16384;
-      s.box  = 0;
-      s.rcpW = 0;
-      if(px0 <= px1 && py0 <= py1)
+      else
       {
-        const int bw = px1 - px0 + 1, bh = py1 - py0 + 1;
-        // padded to a multiple of ITEMS_PER_THREAD so that the items of one thread always belong to one triangle
-        nItems = (uint32_t)(bw * bh + ITEMS_PER_THREAD - 1) & ~(uint32_t)(ITEMS_PER_THREAD - 1);
-        s.box  = (uint32_t)(px0 - tileX0) | ((uint32_t)(py0 - tileY0) << 4) | ((uint32_t)(bw - 1) << 8) | ((uint32_t)(bh - 1) << 12)
-                | (biasBits << 16) | ((zSafe ? 1u : 0u) << 19) | ((small ? 1u : 0u) << 20);
-        s.rcpW = (65535u + bw) / bw;
+        slots[tid].box  = 0u;
+        slots[tid].rcpW = 0u;
       }
-      slots[tid] = s;
     }
     uint32_t total;
     {
