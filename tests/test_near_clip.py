@@ -106,3 +106,29 @@ def test_cuda_matches_oracle_inside_the_sphere_cloud(kw):
     assert np.array_equal(SF.assemble(parts, h, w, 16), o.final)
     s.close()
     o.close()
+
+
+@pytest.mark.gpu
+def test_clip_table_grows():
+    """More pieces than the clip table's initial 4096 entries: the first attempt raises the overflow flag, the table grows
+    and the frame is rendered again (like the pair buffers) -- the result is still the oracle's, bit for bit."""
+    from oracle import oracle_py as O
+    st = oit.State(algorithm=oit.OIT_LOOP64, numObjects=1024, subdiv=16, scaleMin=1.0, scaleWidth=0.0)
+    verts, idx, ipo = oit.generate_scene(st)
+    w, h = 320, 200
+    ubo = oit.default_camera(w, h, eye=(0.0, 0.0, 0.5), center=(0.0, 0.0, -1.0), near=0.05)
+    M = np.array(list(ubo.projViewMatrix), np.float32).reshape(4, 4)
+    zc = verts[:, 0:1] * M[0, 2] + verts[:, 1:2] * M[1, 2] + verts[:, 2:3] * M[2, 2] + M[3, 2]
+    behind = (zc[:, 0] < 0)[idx.reshape(-1, 3)]
+    assert (behind.any(axis=1) & ~behind.all(axis=1)).sum() > 4096          # the scene really needs more entries
+    o, sd = make_oracle(O, st, w, h, verts, idx, ipo, ubo, os.cpu_count() or 1)
+    o.render(sd)
+    s = oit.Sample(st, w, h)
+    s.setScene(verts, idx, ipo)
+    for _ in range(2):
+        s.onRender(ubo)
+        assert np.array_equal(s.readColor(), o.final), f"{(s.readColor() != o.final).sum()} pixels differ"
+    gs = s.stats()
+    assert gs["fragments"] == o.stats["fragments"] and gs["trianglesRejected"] == o.stats["trianglesRejected"]
+    s.close()
+    o.close()
