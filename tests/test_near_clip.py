@@ -43,6 +43,22 @@ def test_oracle_inside_a_closed_surface_every_pixel_once(subdiv, look):
     o.close()
 
 
+def test_oracle_band_threads_agree_on_clipped_scenes():
+    """The oracle's band-parallel mode (what cpu_baseline times) clips per thread: same image as the sequential walk."""
+    from oracle import oracle_py as O
+    st = oit.State(algorithm=oit.OIT_SPINLOCK, aaType=oit.AA_MSAA_4X, numObjects=200, subdiv=6)
+    verts, idx, ipo = oit.generate_scene(st)
+    ubo = oit.default_camera(W, H, eye=(0.2, 0.1, 0.8), center=(0.0, 0.0, -1.0), near=0.05)
+    imgs, frags = [], []
+    for threads in (1, 5):
+        o, sd = make_oracle(O, st, W, H, verts, idx, ipo, ubo, threads)
+        o.render(sd)
+        imgs.append(o.final.copy())
+        frags.append((o.stats["fragments"], o.stats["trianglesRejected"]))
+        o.close()
+    assert np.array_equal(imgs[0], imgs[1]) and frags[0] == frags[1] and frags[0][0] > 0
+
+
 def test_oracle_clipped_scene_differs_from_rejecting(monkeypatch):
     """Sanity of the test itself: the scene really has triangles with vertices behind the near plane."""
     st, verts, idx, ipo, ubo = inside_sphere_scene(2)
