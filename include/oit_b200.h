@@ -238,7 +238,9 @@ int oit_enable_band_gather(OitCtx* ctx, const void* id128);
    resolved pixel straight into ALL bands' frame buffers while it renders (no collective after the frame), and two flag
    rounds per frame (device-side sequence numbers, part of the frame graph) keep the bands in step; OIT_BUF_FRAME holds
    the whole frame on every band once the frame is complete (oit_synchronize).  Every band must call oit_render the same number of times.
-   Tear-down: all bands finish rendering, host barrier, oit_band_peer_disable on every band, host barrier, oit_destroy.
+   Tear-down: all bands finish rendering, host barrier, oit_band_peer_disable on every band (unmaps the other bands'
+   buffers, frees nothing), host barrier, oit_destroy -- or a second oit_band_peer_disable, which releases the exported
+   buffer and leaves the context usable (e.g. to fall back to the NCCL gather when some band could not map its peers).
    Returns OIT_ERR_UNSUPPORTED when the devices cannot map each other's memory (fall back to the NCCL gather above). */
 int oit_band_peer_export(OitCtx* ctx, void* handle64);
 int oit_band_peer_enable(OitCtx* ctx, const void* handles, uint32_t count);

@@ -112,6 +112,7 @@ struct OitCtx
   int    sphSubdiv = 0;
   PeerState* peers     = nullptr;
   bool       peersOpen = false;
+  bool       peersUnmapped = false;  // oit_band_peer_disable has run once: the second call frees the exported buffer
   uint64_t        graphLaunches = 0;
   int        sortedBuf[2]{};
   uint32_t*  hostScalar = nullptr;  // pinned
@@ -1368,15 +1369,19 @@ int oit_band_peer_disable(OitCtx* c)
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
   c->graphValid = false;
-  if(c->peersOpen)
+  if(!c->peersUnmapped)
   {
-    peerClose(c->peers);  // first call: the other bands' buffers are unmapped
-    c->peersOpen = false;
+    // first call, on every band and followed by a host barrier: the other bands' buffers are unmapped (if this band got as
+    // far as mapping them); nothing is freed yet, because other bands may still have THIS band's buffer mapped
+    peerClose(c->peers);
+    c->peersOpen     = false;
+    c->peersUnmapped = true;
     return OIT_OK;
   }
-  peerDestroy(c->peers);  // second call (or export only): the exported buffer itself goes
-  c->peers = nullptr;
-  c->frame = DevBuf{};
+  peerDestroy(c->peers);  // second call: the exported buffer itself goes
+  c->peers         = nullptr;
+  c->peersUnmapped = false;
+  c->frame         = DevBuf{};
   return OIT_OK;
 }
 
