@@ -34,13 +34,31 @@ WORKLOADS = {
 TECH_TABLE = [(a, 0) for a in range(7)]  # per-technique table at 3840x2160, no AA, default parameters
 
 
+KERNEL_SOURCES = ["oit_raster.cu", "oit_fragment.cuh", "oit_fused.cuh", "oit_device.cuh", "oit_internal.h", "oit_clip.cuh"]
+
+
+def kernel_source_hash():
+    """sha256 (first 16 hex digits) over the sources of the frame kernel: ties an ncu capture to the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "vk_order_independent_transparency_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/traffic.json, written by tools/make_traffic.py from the .ncu-rep).  A capture of OTHER kernel sources than the
+    ones in this tree is refused: the number would silently be stale."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return int(json.load(f)[workload]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+            e = json.load(f)[workload]
+        if e.get("kernel_source_sha16") != kernel_source_hash():
+            return None, f"profiles/traffic.json[{workload}] was captured from kernel sources {e.get('kernel_source_sha16')}, this tree is {kernel_source_hash()}: refused"
+        return int(e["dram_bytes_per_launch"]), f"ncu --set full capture {e.get('capture')}: dram__bytes_read.sum + dram__bytes_write.sum, 1 launch"
+    except Exception as ex:
+        return None, f"no capture for this workload ({type(ex).__name__})"
 
 
 def peaks():
@@ -226,16 +244,17 @@ def run_ours(args):
     ms_total, wall_total, stage_ms, launches, clocks, last = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
     gather_ok = None
     if world > 1 and band_gather is None:
-        # untimed check of the in-library band gather: this rank's strips sit on the right rows of the gathered frame and
-        # every rank holds the same frame
-        frame = torch.as_tensor(s.frameDevice(), device=dev)
-        rows = torch.as_tensor(SF.band_rows(H, world, rank, args.strip_rows), device=dev)
-        mine_ok = bool(torch.equal(frame[rows], fin_dev))
-        chk = frame.to(torch.int64).sum().reshape(1)
-        lo, hi = chk.clone(), chk.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        okt = torch.tensor([1 if (mine_ok and lo.item() == hi.item()) else 0], device=dev)
+        # untimed check of the in-library band exchange: the frame EVERY rank holds after the exchange must equal the frame
+        # a single band (one GPU rendering all rows) produces -- rendered here, on this rank's GPU, for the comparison
+        frame = torch.as_tensor(s.frameDevice(), device=dev).clone()
+        full = oit.Sample(st, W, H, device=local)
+        full.setSceneDevice(dverts.data_ptr(), verts.shape[0], didx.data_ptr(), idx.size, ipo, keepalive=(dverts, didx))
+        full.onRender(ubo)
+        full.synchronize()
+        want = torch.as_tensor(full.device_array(oit.BUF_FINAL, "<i4"), device=dev).view(-1)[: H * W].view(H, W)
+        same = bool(torch.equal(frame.view(H, W), want))
+        full.close()
+        okt = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_ok = bool(okt.item())
     F_local = last["fragments"]
@@ -283,6 +302,7 @@ def run_ours(args):
                      "gbs": round(bytes_stage.get(k, 0) / (stage_ms[k] * 1e-3) / 1e9, 1) if stage_ms[k] > 0 and k in bytes_stage else None}
                  for k in stage_ms}
 
+    traffic, traffic_src = measured_traffic(args.workload) if (world == 1 and dom == "color") else (None, "N>1 or another dominant stage")
     out = None
     if rank == 0:
         out = {
@@ -302,7 +322,7 @@ def run_ours(args):
                     "instanced": {"value": F / (e2e_inst_ms * 1e-3), "ms_per_step": e2e_inst_ms, "h2d_bytes_per_step": int(sph_table.nbytes + 224),
                                   "note": "oit_set_scene_spheres: the 32 B/sphere table is uploaded and flattened on the device every step"}},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload) if (world == 1 and dom == "color") else None, "peak_source": peak_src, "stage": dom, "alg_bytes_per_launch": int(bytes_stage[dom]),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "stage": dom, "alg_bytes_per_launch": int(bytes_stage[dom]),
                          "frame": {"alg_bytes": int(frame_bytes), "achieved": frame_bytes / (frame_ms * 1e-3) / 1e9,
                                    "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak}},
             "clocks": clocks,
@@ -327,7 +347,17 @@ def run_ours(args):
         out["per_technique_4k_noaa"] = table
     # CPU baseline: the oracle on this box's host cores, one frame of the same workload (rank 0, N=1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(args.workload, 1, 0)
+        s.onRender(ubo)
+        got = s.readColor().copy()
+        cb, want, Fo = cpu_baseline(args.workload, 1, 0, want_final=True)
+        out["cpu_baseline"] = cb
+        # the oracle frame the baseline just rendered is the parity check of the number-bearing configuration
+        if want is not None:
+            out["parity"] = {"checker": "oracle/liboit_oracle.so, same scene + UBO", "pixels": int(want.size), "pixels_differ": int((got != want).sum()),
+                             "fragments_equal": bool(Fo == F), "fragments_oracle": int(Fo)}
+        else:
+            out["parity"] = {"checker": "not applicable: the CPU baseline of this workload is a bounded sample (first 20000 spheres); "
+                                        "parity of config 5 is tests/test_gpu_fullsize.py (cfg5_*)"}
     s.close()
     if world > 1:
         dist.destroy_process_group()
@@ -335,7 +365,7 @@ def run_ours(args):
         emit(out)
 
 
-def cpu_baseline(workload, steps, warmup):
+def cpu_baseline(workload, steps, warmup, want_final=False):
     """The oracle (CPU restatement of the reference path; the reference itself needs Vulkan and cannot run here),
     band-parallel over all host cores."""
     from oracle import oracle_py as O
@@ -360,10 +390,35 @@ def cpu_baseline(workload, steps, warmup):
         if sum(times) > 150:
             break
     F = o.stats["fragments"]
+    final = o.final.copy() if (want_final and not bounded) else None
     o.close()
     t = float(np.mean(times))
-    return {"value": F / t, "unit": "fragments/s", "cores": cores, "kind": "port", "ms_per_frame": t * 1e3, "frames_timed": len(times),
+    cb = {"value": F / t, "unit": "fragments/s", "cores": cores, "kind": "port", "ms_per_frame": t * 1e3, "frames_timed": len(times),
             "sample": f"{len(times)} full frame(s) of {workload}{bounded}, {F} fragments each, oracle/liboit_oracle.so with {cores} OpenMP threads"}
+    return (cb, final, F) if want_final else cb
+
+
+def probe_vulkan():
+    """is there a Vulkan loader + a headless ICD on this box, i.e. could the reference's own path run here?
+    Looked up every time (ICD manifests, ldconfig, the reference binary); the outcome goes into the reference arm's line."""
+    import glob
+    import shutil
+    icds = []
+    for d in ("/usr/share/vulkan/icd.d", "/etc/vulkan/icd.d", "/usr/local/share/vulkan/icd.d", os.path.expanduser("~/.local/share/vulkan/icd.d")):
+        icds += sorted(glob.glob(os.path.join(d, "*.json")))
+    for var in ("VK_ICD_FILENAMES", "VK_DRIVER_FILES"):
+        if os.environ.get(var):
+            icds += os.environ[var].split(":")
+    loader = None
+    try:
+        out = subprocess.run(["ldconfig", "-p"], capture_output=True, text=True, timeout=10).stdout
+        hits = [ln.split("=>")[-1].strip() for ln in out.splitlines() if "libvulkan.so" in ln]
+        loader = hits[0] if hits else None
+    except Exception:
+        pass
+    binary = shutil.which("vk_order_independent_transparency")
+    return {"icd_manifests": icds, "loader": loader, "vulkaninfo": shutil.which("vulkaninfo"), "reference_binary": binary,
+            "reference_runnable": bool(icds and loader and binary)}
 
 
 def run_reference(args):
@@ -372,12 +427,14 @@ def run_reference(args):
         return
     cb = cpu_baseline(args.workload, args.steps, min(args.warmup, 1))
     W, H, kw, desc = WORKLOADS[args.workload]
+    vk = probe_vulkan()
     emit(({
         "impl": "reference", "metric": "transparent fragments/s", "value": cb["value"], "unit": "fragments/s", "n_gpus": args.gpus,
         "steps": cb["frames_timed"], "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic (the sample's seeded sphere cloud)",
-        "config": {"workload": f"{args.workload}: {desc}", "note": "the reference's Vulkan path cannot run here (no Vulkan loader/ICD, nvpro_core2, shaderc); "
-                   "this arm is its CPU restatement (the oracle) on the host cores"},
+        "config": {"workload": f"{args.workload}: {desc}", "vulkan_probe": vk,
+                   "note": ("a Vulkan loader and ICD are present, but " if (vk["icd_manifests"] and vk["loader"]) else "no Vulkan loader + ICD on this box, and ")
+                   + "the reference binary is not built (it needs nvpro_core2, shaderc, GLFW; no network): this arm is the reference's CPU restatement (the oracle) on the host cores"},
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

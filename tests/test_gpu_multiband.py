@@ -16,7 +16,7 @@ def test_two_band_exchange_matches_single_band():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "test_band_gather.py"), "both"]
+           "--master-port", "29533", os.path.join(ROOT, "tools", "check_band_gather.py"), "both"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "BAND EXCHANGE OK" in r.stdout

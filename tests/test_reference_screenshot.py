@@ -7,8 +7,12 @@ tail blend, 1024 spheres of subdivision 16, the default camera, a 1920 x 1017 vi
 What matches: the scene generator (sphere placement, radii, colours, argument evaluation order), the camera and
 projection, rasterisation and 4x MSAA coverage, the Interlock k-buffer with 16 layers + tail blending, the sort and
 blend arithmetic, sRGB encoding and the MSAA resolve.  Tolerance (the reference ran on a hardware rasteriser / ROP, the
-GLSL compiler contracts multiply-adds, and ties in Interlock's racy ordering may differ): mean absolute difference
-<= 0.5 / 255, >= 65 % of the pixels identical, <= 0.1 % of the pixels off by more than 8 / 255, none by more than 48."""
+GLSL compiler contracts multiply-adds, and ties in Interlock's racy ordering may differ).  The assertion is what is
+ACHIEVED (oracle and CUDA path alike, they are bit-identical): >= 99.5 % of the pixels within 1 LSB of every RGB channel
+(measured 99.58 %), >= 70 % identical (71.3 %), mean absolute difference <= 0.15 / 255 (0.13), <= 0.02 % of the pixels
+off by more than 8 / 255, none by more than 32 (worst 27).  north_star's bar for this check is 99.9 % within 1 LSB
+against the reference's own render of the same frame: NOT met by 0.32 % of the pixels -- all on sphere silhouettes, where
+a hardware rasteriser's sub-pixel snapping / a ROP's blend rounding decide a sample differently."""
 import os
 import sys
 
@@ -42,8 +46,9 @@ def check_against_screenshot(final_bgra):
     img, mask = screenshot()
     rgb = oit.bgra_to_rgba_image(final_bgra)[1:, :, :3].astype(np.int32)   # the capture starts at viewport row 1
     d = np.abs(rgb - img).max(axis=-1)[mask]
-    stats = dict(mean=float(np.abs(rgb - img)[mask].mean()), identical=float((d == 0).mean()), over8=float((d > 8).mean()), worst=int(d.max()))
-    assert stats["mean"] <= 0.5 and stats["identical"] >= 0.65 and stats["over8"] <= 1e-3 and stats["worst"] <= 48, stats
+    stats = dict(mean=float(np.abs(rgb - img)[mask].mean()), identical=float((d == 0).mean()), within1=float((d <= 1).mean()),
+                 over8=float((d > 8).mean()), worst=int(d.max()))
+    assert stats["within1"] >= 0.995 and stats["identical"] >= 0.70 and stats["mean"] <= 0.15 and stats["over8"] <= 2e-4 and stats["worst"] <= 32, stats
     return stats
 
 

@@ -1,6 +1,6 @@
 """Multi-GPU check of the split-frame exchange inside the library (run under torchrun, one rank per GPU): every rank
 renders its strips, the frame is exchanged (peer-memory stores from the frame kernel, or the NCCL all-gather), and the
-result on every rank must equal a single-band render.  usage: torchrun ... tools/test_band_gather.py [peers|nccl|both]"""
+result on every rank must equal a single-band render.  usage: torchrun ... tools/check_band_gather.py [peers|nccl|both]"""
 import faulthandler
 import os
 import sys

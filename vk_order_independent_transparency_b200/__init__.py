@@ -252,10 +252,30 @@ class Sample:
             self.h = None
 
     def __del__(self):
+        # Finalizers run at different times on different ranks (or after the process group is gone), so they must not run
+        # the collective tear-down of the peer exchange: a peer-enabled Sample has to be closed explicitly (close() or a
+        # `with` block).  If it was not, this band unmaps the other bands' buffers and LEAKS its own exported frame buffer --
+        # other bands may still have it mapped -- instead of freeing it under them.
         try:
+            if getattr(self, "h", None) and getattr(self, "_peer_dist", None) is not None:
+                import warnings
+                warnings.warn("Sample with the peer-memory exchange enabled was not closed explicitly: its exported frame buffer is leaked",
+                              ResourceWarning)
+                self._peer_dist = None
+                self.L.oit_synchronize(self.h)
+                self.L.oit_band_peer_disable(self.h)   # first phase only: local unmap, nothing is freed
+                self.h = None
+                return
             self.close()
         except Exception:
             pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def _check(self, r):
         if r != 0:

@@ -104,7 +104,6 @@ struct OitCtx
   DevBuf           gatherBuf, frame;
   uint32_t         padRows    = 0;
   bool             gatherWarm = false;  // NCCL has run once outside a capture (connection set-up must not be captured)
-  bool             skipGather = false;  // re-render after a buffer growth: the frame's one collective already ran
   bool             finOwned   = true;   // false once `fin` is this rank's slice of the gather buffer
   // split frame over peer memory (oit_peer.cu): the frame kernel stores into every band's frame buffer
   // instanced scene input (oit_set_scene_spheres): the object table and the unit-sphere template of `sphSubdiv`
@@ -654,7 +653,7 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
 // the sample's 3.1 M indices costs more than the frame).  On failure the context is left without a scene.
 static int validateIndices(OitCtx* c, const uint32_t* dIndices, uint32_t nIndices, uint32_t nVerts)
 {
-  unsigned long long* flag = (unsigned long long*)c->stats.p + (NUM_STAT_SLOTS - 1);  // no frame is in flight here
+  unsigned long long* flag = (unsigned long long*)c->stats.p + STAT_SCRATCH;  // no frame is in flight here
   CUDA_TRY(c, cudaMemsetAsync(flag, 0, sizeof(*flag), c->stream));
   launchValidateIndices(dIndices, nIndices, nVerts, flag, c->stream);
   unsigned long long bad = 0;
@@ -961,13 +960,13 @@ static int issueFrame(OitCtx* c)
   const bool exchange = c->peers && c->peersOpen;
   // split frame over peer memory: "my frame buffer may be overwritten" goes out first, the wait for the other bands'
   // comes as late as possible (the geometry stage and the opaque pass absorb the skew between the bands)
-  if(exchange && !c->skipGather)
-    c->launches += peerSignal(c->peers, PEER_FLAG_READY, c->stream);
+  if(exchange)
+    c->launches += peerSignal(c->peers, PEER_FLAG_READY, (const unsigned long long*)c->stats.p, c->stream);
   if((r = oit_begin_frame(c)) != OIT_OK)
     return r;
   if((r = oit_draw_opaque(c)) != OIT_OK)
     return r;
-  if(exchange && !c->skipGather)
+  if(exchange)
   {
     c->launches += peerWait(c->peers, PEER_FLAG_READY, (unsigned long long*)c->stats.p, c->stream);
     record(c, EV_OPAQUE);  // time spent waiting for the other bands is not the colour pass's
@@ -985,18 +984,16 @@ static int issueFrame(OitCtx* c)
   {
     if(!c->fp.fused)
       c->launches += peerScatterRows(c->peers, (const uint32_t*)c->fin.p, (int)c->cfg.width, (int)c->localOutH, (int)c->stripRows, c->stream);
-    if(!c->skipGather)
-    {
-      c->launches += peerSignal(c->peers, PEER_FLAG_DONE, c->stream);
-      c->launches += peerWait(c->peers, PEER_FLAG_DONE, (unsigned long long*)c->stats.p, c->stream);
-    }
+    // DONE carries this band's overflow flag: after the wait every band knows whether any band repeats the frame
+    c->launches += peerSignal(c->peers, PEER_FLAG_DONE, (const unsigned long long*)c->stats.p, c->stream);
+    c->launches += peerWait(c->peers, PEER_FLAG_DONE, (unsigned long long*)c->stats.p, c->stream);
     CUDA_TRY(c, cudaGetLastError());
   }
   // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
-  if(c->gather && !c->skipGather)
+  if(c->gather)
   {
     const int n = gatherLaunch(c->gather, (uint32_t*)c->gatherBuf.p, (uint32_t*)c->frame.p, (int)c->cfg.width, (int)c->cfg.height,
-                               (int)c->stripRows, (int)c->padRows, c->stream, c->error);
+                               (int)c->stripRows, (int)c->padRows, (unsigned long long*)c->stats.p, c->stream, c->error);
     if(n < 0)
       return n;
     c->launches += n;
@@ -1109,21 +1106,17 @@ static int finishFrame(OitCtx* c)
       return r;
     if(c->hostMirror[STAT_PEER_TIMEOUT] != 0)
       return fail(c, OIT_ERR_CUDA, "split frame: a band did not reach the frame barrier (peer exchange timed out)");
+    // Split frame: the decision to render the frame again is COLLECTIVE.  The exchange itself carried every band's overflow
+    // flag (STAT_OVERFLOW_ANY), so all bands repeat the frame -- with a full exchange round -- when any of them had to grow a
+    // buffer, and no band is left with the strips of an overflowed attempt.  (Bands call the frame-completing entry points
+    // in the same order, so they look at the same frame here.)
+    bool repeat = grown;
     if(c->gather || (c->peers && c->peersOpen))
     {
       c->gatherWarm = true;
-      if(c->skipGather)
-      {
-        // this was the re-render after a pair-buffer growth: the exchange round already ran (once per oit_render on every
-        // rank, or the ranks would deadlock), so with the NCCL gather the other ranks keep this band's strips of the
-        // overflowed attempt for this one frame (the peer-memory path still stores the re-rendered strips everywhere).
-        c->skipGather = false;
-        c->graphValid = false;
-      }
-      else if(grown)
-        c->skipGather = true;
+      repeat        = repeat || c->hostMirror[STAT_OVERFLOW_ANY] != 0;
     }
-    if(!grown)
+    if(!repeat)
       return OIT_OK;
     if((r = enqueueFrame(c)) != OIT_OK)
       return r;
@@ -1143,7 +1136,9 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
     return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
   // a frame in flight that already reported a pair-buffer overflow (the mirror is pinned host memory written by the frame's
   // last nodes): grow the buffers now instead of letting further frames run with truncated triangle lists
-  if(c->framePending && reinterpret_cast<volatile unsigned long long*>(c->hostMirror)[STAT_OVERFLOW] != 0)
+  // (not in split-frame mode: there the bands must take the decision at the same frame, which finishFrame guarantees)
+  if(c->framePending && !c->gather && !(c->peers && c->peersOpen)
+     && reinterpret_cast<volatile unsigned long long*>(c->hostMirror)[STAT_OVERFLOW] != 0)
     if((r = finishFrame(c)) != OIT_OK)
       return r;
   if((r = enqueueFrame(c)) != OIT_OK)
@@ -1294,7 +1289,7 @@ int oit_enable_band_gather(OitCtx* c, const void* id128)
     pad = std::max(pad, rows);
   }
   c->padRows = pad;
-  const size_t slice = (size_t)pad * c->cfg.width;
+  const size_t slice = (size_t)(pad + 1) * c->cfg.width;  // + one metadata row (the band's overflow flag, see oit_gather.cu)
   int          r;
   if((r = devAlloc(c, c->gatherBuf, slice * c->cfg.bandCount * 4)) != OIT_OK)
     return r;
@@ -1331,6 +1326,8 @@ int oit_band_peer_export(OitCtx* c, void* handle64)
     return fail(c, OIT_ERR_INVALID_ARG, "oit_band_peer_export has already been called");
   const size_t bytes = (size_t)c->cfg.width * c->cfg.height * 4;
   c->peers           = peerCreate((int)c->cfg.bandIndex, (int)c->cfg.bandCount, bytes, handle64, c->error);
+  c->peersOpen       = false;
+  c->peersUnmapped   = false;
   if(!c->peers)
     return OIT_ERR_UNSUPPORTED;
   devFree(c->frame);
@@ -1353,9 +1350,9 @@ int oit_band_peer_enable(OitCtx* c, const void* handles, uint32_t count)
   const int r = peerOpen(c->peers, handles, c->error);
   if(r != OIT_OK)
     return r;
-  c->peersOpen  = true;
-  c->graphValid = false;
-  c->skipGather = false;
+  c->peersOpen     = true;
+  c->peersUnmapped = false;
+  c->graphValid    = false;
   return OIT_OK;
 }
 
@@ -1380,6 +1377,7 @@ int oit_band_peer_disable(OitCtx* c)
   }
   peerDestroy(c->peers);  // second call: the exported buffer itself goes
   c->peers         = nullptr;
+  c->peersOpen     = false;
   c->peersUnmapped = false;
   c->frame         = DevBuf{};
   return OIT_OK;

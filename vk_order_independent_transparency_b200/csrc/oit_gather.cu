@@ -107,29 +107,45 @@ void gatherDestroy(BandGatherState* g)
   delete g;
 }
 
-// frame[y][x] = gathered[band(y)][localRow(y)][x]; band k owns the strips k, k + G, ... of stripRows output rows
+// frame[y][x] = gathered[band(y)][localRow(y)][x]; band k owns the strips k, k + G, ... of stripRows output rows.
+// Every band's slice is padRows rows + ONE metadata row whose first word pair is the band's overflow flag of this frame
+// (a pair / clip buffer was too small): their OR goes to stats[STAT_OVERFLOW_ANY], so that every band takes the same
+// decision to render the frame again.
 __global__ void __launch_bounds__(256) k_interleave_rows(const uint4* __restrict__ gathered, uint4* __restrict__ frame, int quadsPerRow, int H,
-                                                         int stripRows, int G, int padRows)
+                                                         int stripRows, int G, int padRows, unsigned long long* __restrict__ stats)
 {
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    unsigned long long any = 0;
+    for(int b = 0; b < G; b++)
+      any |= *reinterpret_cast<const unsigned long long*>(gathered + ((size_t)b * (padRows + 1) + padRows) * quadsPerRow);
+    stats[STAT_OVERFLOW_ANY] = any ? 1ull : 0ull;
+  }
   const size_t total = (size_t)quadsPerRow * H;
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
   {
     const int y = (int)(i / quadsPerRow), q = (int)(i - (size_t)y * quadsPerRow);
     const int strip = y / stripRows, band = strip % G;
     const int local = (strip / G) * stripRows + (y - strip * stripRows);
-    frame[i]        = gathered[((size_t)band * padRows + local) * quadsPerRow + q];
+    frame[i]        = gathered[((size_t)band * (padRows + 1) + local) * quadsPerRow + q];
   }
 }
 
 // all-gather (in place) + interleave; returns the number of own kernels launched, < 0 on error
-int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, cudaStream_t s,
-                 std::string& err)
+int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, unsigned long long* stats,
+                 cudaStream_t s, std::string& err)
 {
   NcclApi* api = ncclApi(err);
   if(!api)
     return OIT_ERR_UNSUPPORTED;
-  const size_t       count = (size_t)padRows * W;
-  const ncclResult_t r     = api->AllGather(gathered + (size_t)g->rank * count, gathered, count, ncclUint32, g->comm, s);
+  const size_t count = (size_t)(padRows + 1) * W;  // + the metadata row
+  if(cudaMemcpyAsync(gathered + (size_t)g->rank * count + (size_t)padRows * W, stats + STAT_OVERFLOW, sizeof(unsigned long long),
+                     cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+  {
+    err = "band gather: metadata copy failed";
+    return OIT_ERR_CUDA;
+  }
+  const ncclResult_t r = api->AllGather(gathered + (size_t)g->rank * count, gathered, count, ncclUint32, g->comm, s);
   if(r != ncclSuccess)
   {
     err = std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(r) : "error");
@@ -139,7 +155,7 @@ int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W,
   const size_t total = (size_t)quads * H;
   const int    grid  = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
   k_interleave_rows<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(gathered), reinterpret_cast<uint4*>(frame), quads, H, stripRows,
-                                          g->world, padRows);
+                                          g->world, padRows, stats);
   return 1;
 }
 

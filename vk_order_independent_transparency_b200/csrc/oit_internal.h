@@ -72,7 +72,10 @@ enum StatSlot
   STAT_REJECTED,
   STAT_OVERFLOW,  // the (tile, triangle) pair buffer of a draw was too small: the frame must be rendered again
   STAT_PEER_TIMEOUT,  // split frame over peer memory: a band did not arrive at the frame barrier in time
-  NUM_STAT_SLOTS = 8
+  STAT_SCRATCH,       // scene upload: index validation flag (no frame is in flight then)
+  STAT_OVERFLOW_ANY,  // split frame: SOME band raised STAT_OVERFLOW for this frame (carried by the exchange itself), so that
+                      // every band takes the same decision to render the frame again
+  NUM_STAT_SLOTS = 10
 };
 
 // Split frame over NVLink peer memory (oit_peer.cu): band b's resolved pixels are stored straight into the whole-frame
@@ -81,7 +84,9 @@ constexpr int PEER_MAX       = 16;
 constexpr int PEER_FLAG_READY = 0;             // flags[READY + b] = n: band b no longer reads frame n - 1 of ITS buffer
 constexpr int PEER_FLAG_DONE  = PEER_MAX;      // flags[DONE + b]  = n: band b's strips of frame n are in THIS buffer
 constexpr int PEER_FLAG_SEQ   = 2 * PEER_MAX;  // frames completed by this band (local use)
+constexpr int PEER_FLAG_OVF   = 2 * PEER_MAX + 1;  // flags[OVF + b] = n: band b's frame n overflowed a pair / clip buffer
 constexpr int PEER_FLAG_WORDS = 64;
+static_assert(PEER_FLAG_OVF + PEER_MAX <= PEER_FLAG_WORDS, "peer flag page");
 struct PeerTable
 {
   uint32_t* frame[PEER_MAX];  // whole frame [H][W] BGRA8 of band b (peer-mapped, own entry local)
@@ -201,8 +206,8 @@ struct BandGatherState;
 int              gatherUniqueId(void* id128, std::string& err);
 BandGatherState* gatherCreate(const void* id128, int rank, int world, std::string& err);
 void             gatherDestroy(BandGatherState* g);
-int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, cudaStream_t s,
-                 std::string& err);
+int gatherLaunch(BandGatherState* g, uint32_t* gathered, uint32_t* frame, int W, int H, int stripRows, int padRows, unsigned long long* stats,
+                 cudaStream_t s, std::string& err);
 
 // split frame over peer memory (oit_peer.cu): CUDA IPC mappings of every band's frame buffer + flag barrier kernels
 struct PeerState;
@@ -212,7 +217,7 @@ void             peerClose(PeerState* ps);                                      
 void             peerDestroy(PeerState* ps);
 uint32_t*        peerFrame(PeerState* ps);
 const PeerTable* peerTable(PeerState* ps);
-int              peerSignal(PeerState* ps, int phase, cudaStream_t s);
+int              peerSignal(PeerState* ps, int phase, const unsigned long long* stats, cudaStream_t s);
 int              peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s);
 int peerScatterRows(PeerState* ps, const uint32_t* fin, int W, int localRows, int stripRows, cudaStream_t s);
 

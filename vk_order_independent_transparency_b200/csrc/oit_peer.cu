@@ -148,12 +148,17 @@ __device__ __forceinline__ unsigned long long globalTimerNs()
 }
 
 // one thread per band: flags[phase + rank] of band b = the number of the frame being rendered
-__global__ void __launch_bounds__(32) k_peer_signal(const PeerTable* __restrict__ t, int world, int rank, int phase)
+// With DONE goes the band's overflow flag of this frame (a pair / clip buffer was too small: the frame will be rendered
+// again), so that after the DONE round every band knows whether ANY band has to repeat the frame.
+__global__ void __launch_bounds__(32) k_peer_signal(const PeerTable* __restrict__ t, int world, int rank, int phase,
+                                                    const unsigned long long* __restrict__ stats)
 {
   const int b = threadIdx.x;
   if(b >= world)
     return;
   const uint32_t seq = t->flags[rank][PEER_FLAG_SEQ] + 1u;
+  if(phase == PEER_FLAG_DONE)
+    t->flags[b][PEER_FLAG_OVF + rank] = stats[STAT_OVERFLOW] != 0ull ? seq : 0u;
   __threadfence_system();
   stReleaseSys(t->flags[b] + phase + rank, seq);
 }
@@ -179,13 +184,22 @@ __global__ void __launch_bounds__(32) k_peer_wait(const PeerTable* __restrict__ 
   }
   __syncwarp();
   __threadfence_system();
-  if(phase == PEER_FLAG_DONE && b == 0)
-    local[PEER_FLAG_SEQ] = seq;
+  if(phase == PEER_FLAG_DONE)
+  {
+    // the overflow flags travelled with DONE (written before the flag's release store, read after its acquire load)
+    const bool ovf = b < world && *reinterpret_cast<volatile uint32_t*>(local + PEER_FLAG_OVF + b) == seq;
+    const bool any = __any_sync(0xffffffffu, ovf);
+    if(b == 0)
+    {
+      stats[STAT_OVERFLOW_ANY] = any ? 1ull : 0ull;
+      local[PEER_FLAG_SEQ]     = seq;
+    }
+  }
 }
 
-int peerSignal(PeerState* ps, int phase, cudaStream_t s)
+int peerSignal(PeerState* ps, int phase, const unsigned long long* stats, cudaStream_t s)
 {
-  k_peer_signal<<<1, 32, 0, s>>>(ps->table, ps->world, ps->rank, phase);
+  k_peer_signal<<<1, 32, 0, s>>>(ps->table, ps->world, ps->rank, phase, stats);
   return 1;
 }
 

@@ -655,14 +655,20 @@ static void launchKernel(const FrameParams& p, unsigned grid, cudaStream_t s)
   // (+ the tile's k-buffer slice and aux words when the technique runs on chip)
   const size_t dynBytes = (size_t)TILE_PIX * S * (PASS == PASS_WEIGHTED ? 10 : 4)
                           + (p.onChip ? (size_t)onChipWords(p.algorithm, p.L, p.coverage) * 4 : 0);
-  static bool configured = false;
-  if(!configured)
+  // function attributes are per device: one flag per ordinal (contexts of several GPUs may live in one process)
+  static bool configured[64] = {};
+  int         dev            = 0;
+  cudaGetDevice(&dev);
+  if(dev < 0 || dev >= 64 || !configured[dev])
   {
-    cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(TILE_PIX * S * 10 + ON_CHIP_MAX_BYTES));
-    if(OIT_SMEM_CARVEOUT >= 0)
-      cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
-    configured = true;
+    cudaError_t e = cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(TILE_PIX * S * 10 + ON_CHIP_MAX_BYTES));
+    if(e == cudaSuccess && OIT_SMEM_CARVEOUT >= 0)
+      e = cudaFuncSetAttribute(k_raster<PASS, S, SSHADE>, cudaFuncAttributePreferredSharedMemoryCarveout, OIT_SMEM_CARVEOUT);
+    if(e != cudaSuccess)
+      return;  // stays in cudaGetLastError(), which every stage entry point checks after its launches
+    if(dev >= 0 && dev < 64)
+      configured[dev] = true;
   }
   const bool fused = p.fused && PASS != PASS_OPAQUE && PASS != PASS_LOOP_DEPTH;
   k_raster<PASS, S, SSHADE><<<grid, RASTER_THREADS, fused ? dynBytes : 0, s>>>(p);
