@@ -29,6 +29,8 @@
 // Tuning record (B200, 4K 8x MSAA linked list; profiles/README.md): 256 threads x 5 CTAs / SM (48 registers) beats 4 x 64
 // registers and 128-thread CTAs; 4 items per thread beats 2 and 8; __match_any_sync bucketing beats ballots; per-pixel
 // sequence counters with spin-waits instead of the per-layer barriers were slower (two block fences per fragment).
+#include <cstdlib>
+
 #include "oit_raster_common.cuh"
 
 namespace oit {
@@ -465,6 +467,13 @@ static void launchPass(const FrameParams& p, cudaStream_t s)
   }
 }
 
+// OIT_B200_LAYERED_LL=1: the linked list through the generic primitive-ordered kernel (A/B comparisons, tests)
+static bool useLayeredLinkedList()
+{
+  static const bool v = getenv("OIT_B200_LAYERED_LL") != nullptr;
+  return v;
+}
+
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s)
 {
   if(p.tilesX * p.tileRowsLocal == 0)
@@ -472,7 +481,12 @@ int launchRaster(const FrameParams& p, int pass, cudaStream_t s)
   switch(pass)
   {
     case PASS_SIMPLE: launchPass<PASS_SIMPLE>(p, s); break;
-    case PASS_LINKEDLIST: launchPass<PASS_LINKEDLIST>(p, s); break;
+    case PASS_LINKEDLIST:
+      // without sample shading the linked list has its own order-free kernel (oit_raster_ll.cu)
+      if(!p.sampleShading && !useLayeredLinkedList())
+        return launchRasterLinkedList(p, s);
+      launchPass<PASS_LINKEDLIST>(p, s);
+      break;
     case PASS_LOOP_COLOR: launchPass<PASS_LOOP_COLOR>(p, s); break;
     case PASS_LOOP64: launchPass<PASS_LOOP64>(p, s); break;
     case PASS_SPINLOCK: launchPass<PASS_SPINLOCK>(p, s); break;

@@ -1,0 +1,408 @@
+// oit_raster_ll.cu -- the Linked List colour pass (K4, oitLinkedList.frag.glsl:51-85) as an ORDER-FREE tile kernel, fused
+// with the tile's composite (K5, oitLinkedList.frag.glsl:106-172) and resolve when oit_render asks for it.
+//
+// What the list needs from "primitive order" is only the ORDER OF THE LINKS: fragment k of a pixel points to fragment k-1.
+// That order is known before anything is shaded, so nothing has to be serialised:
+//
+//   A  coverage   each thread tests ITEMS_PER_THREAD (triangle, pixel) candidates (oit_raster_common.cuh).  A covered
+//                 fragment sets bit `triangle slot` in its pixel's 128-bit set (one chunk = 128 staged triangles, so the
+//                 bit index IS the primitive order) and is appended to an unordered compact list.
+//   B  allocate   thread = pixel: popcount of the set = fragments of the pixel in this batch; one CTA scan gives every pixel
+//                 a contiguous range of the batch's nodes, ONE atomicAdd per batch on the global counter (the reference
+//                 issues one per fragment, oitLinkedList.frag.glsl:55) reserves them, and the pixel's head moves to the last.
+//   C  shade      dense over the compact list, any order: rank of the fragment among its pixel's = popcount of the lower
+//                 bits; node = base + pixel offset + rank; next = node - 1 (rank > 0) or the pixel's previous head.  Shade,
+//                 pack, ONE 128-bit store.  No tickets, no layers, no per-fragment atomics, no barrier per layer.
+//
+// Three CTA barriers per batch of up to 1024 candidates.  The list heads of the tile live in shared memory for the whole
+// pass (written to imgAux once at the end); the lists are identical to the ones the sequential schedule builds (same
+// nodes per pixel in the same link order; node NUMBERS differ, like between any two runs of the reference).
+//
+// Pool overflow (node index >= capacity, oitLinkedList.frag.glsl:82): the overflowing fragments are tail-blended by the
+// ROP in primitive order.  The batch then takes a slower path: the fragments are permuted into pixel-major order, shaded
+// densely in rounds of 256 into a small shared-memory queue, and each pixel's owner thread blends its fragments in order.
+#include "oit_raster_common.cuh"
+
+namespace oit {
+
+constexpr int LL_CHUNK     = 128;  // triangles staged per chunk = bits of a pixel's per-batch triangle set
+constexpr int LL_IPT       = ITEMS_PER_THREAD;
+constexpr int LL_BATCH     = RASTER_THREADS * LL_IPT;
+#ifndef OIT_LL_MIN_BLOCKS
+#define OIT_LL_MIN_BLOCKS 5
+#endif
+
+template <int S>
+__global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll(const FrameParams p)
+{
+  static_assert(RASTER_THREADS == TILE_PIX, "phase B maps one thread to one pixel of the tile");
+  // per-chunk / per-batch structures; dead once the tile's list has been walked, when the fused composite reuses the space
+  constexpr size_t SLOT_BYTES = sizeof(TriSlot) * LL_CHUNK;
+  constexpr size_t SET_BYTES  = sizeof(uint4) * TILE_PIX * 2;        // per-pixel triangle sets of two consecutive batches
+  constexpr size_t LIST_BYTES = sizeof(uint32_t) * LL_BATCH * 2;     // compact fragment lists of two consecutive batches
+  constexpr size_t WORK_BYTES = SLOT_BYTES + SET_BYTES + LIST_BYTES;
+  constexpr size_t SCRATCH_BYTES = WORK_BYTES > sizeof(FusedArrays) ? WORK_BYTES : sizeof(FusedArrays);
+  static_assert(SLOT_BYTES % 16 == 0, "alignment of the sets");
+  __shared__ __align__(16) unsigned char scratch[SCRATCH_BYTES];
+  __shared__ SrgbTables tabs;
+  __shared__ uint32_t   itemStart[LL_CHUNK + 1];
+  __shared__ uint32_t   headSm[TILE_PIX];    // list head of every pixel of the tile
+  __shared__ uint32_t   prevHead[TILE_PIX];  // ... before the current batch
+  __shared__ uint32_t   pixOff[TILE_PIX];    // first node (relative to the batch's base) of the pixel's fragments
+  __shared__ uint32_t   pixPre[TILE_PIX];    // fragments in set words 0..w-1, one byte per word w
+  __shared__ uint32_t   warpTot[RASTER_THREADS / 32];
+  __shared__ uint32_t   sCount[2];
+  __shared__ uint32_t   sBase;
+  __shared__ uint32_t   scanSm[33];
+  __shared__ uint8_t    tailMask[RASTER_THREADS];
+  extern __shared__ __align__(16) unsigned char dynSmem[];  // fused frame: the tile's colour samples
+  TriSlot*  slots   = reinterpret_cast<TriSlot*>(scratch);
+  uint4*    pixSet  = reinterpret_cast<uint4*>(scratch + SLOT_BYTES);
+  uint32_t* lists   = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES + SET_BYTES);
+
+  const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = p.tileOrder[blockIdx.x];  // launch order: longest lists first
+  const uint32_t listBegin = p.tileStart[tile], listEnd = p.tileStart[tile + 1];
+  const bool     fused = p.fused != 0;
+  if(listBegin == listEnd && !fused)
+    return;
+  const int rl = tile / p.tilesX, tx = tile - rl * p.tilesX;
+  const int R  = tileRowToGlobal(rl, p.stripTileRows, p.bandCount, p.bandIndex);
+  const int tileX0 = tx * TILE_W, tileY0 = R * TILE_H;  // global pixel origin of the tile
+  const int yLocal0 = rl * TILE_H;                      // the same row inside this band's buffers
+  // the pixel this thread owns in phase B
+  const int    ownX = tileX0 + (tid & (TILE_W - 1)), ownLy = tid >> TILE_SHIFT;
+  const bool   ownValid = ownX < p.W && tileY0 + ownLy < p.H;
+  const size_t ownPix   = (size_t)(yLocal0 + ownLy) * p.W + ownX;
+
+  uint32_t* tileColorSm = reinterpret_cast<uint32_t*>(dynSmem);
+  uint32_t* tileColor   = fused ? tileColorSm : nullptr;
+  const bool emptyTile  = listBegin == listEnd;
+  if(fused)
+  {
+    // the tile's colour samples start as the cleared (or opaque-drawn) m_colorImage content
+    for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
+    {
+      const int pl = i / S, gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
+      uint32_t  v  = p.clearColor;
+      if(p.depth != nullptr && gx < p.W && tileY0 + ly < p.H)
+        v = p.color[((size_t)(yLocal0 + ly) * p.W + gx) * S + (i - pl * S)];
+      tileColorSm[i] = v;
+    }
+  }
+  loadTables(tabs, p.tables);
+  headSm[tid] = (ownValid && !emptyTile) ? p.aux[ownPix] : 0u;
+  if(!emptyTile)
+  {
+    pixSet[tid]            = make_uint4(0u, 0u, 0u, 0u);
+    pixSet[TILE_PIX + tid] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if(tid < 2)
+    sCount[tid] = 0u;
+  uint32_t  nFrag = 0, nStored = 0, nTail = 0;
+  uint32_t  parity = 0;
+  const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16);  // samples sit in [lo, 256 - lo] of the pixel
+  uint4*    nodes = reinterpret_cast<uint4*>(p.abuf);
+  __syncthreads();
+
+  // shading of one fragment record at the pixel centre (coverage shading / no AA: SURVEY 8a row R) -> packed colour, depth
+  auto shadeRecord = [&](uint32_t rec, Color4& rgba, float& z) {
+    const TriSlot& s     = slots[rec & (LL_CHUNK - 1)];
+    const bool     small = (s.box >> 20) & 1u;
+    const int      lx = (rec >> 8) & 15, ly = (rec >> 12) & 15;
+    const int      cx = ((tileX0 + lx) << 8) + 128, cy = ((tileY0 + ly) << 8) + 128;
+    const Bary     bc = makeBary(edgeFloat(s, 1, cx, cy, small), edgeFloat(s, 2, cx, cy, small), s.rarea);
+    float          vz = 0.f;
+    rgba              = shadeAt<false>(p, s, bc, vz);
+    z                 = depthAt(s, bc);
+  };
+
+  for(uint32_t base = listBegin; base < listEnd; base += LL_CHUNK)
+  {
+    // ---- stage: one triangle per thread (the first LL_CHUNK threads) -------------------------------------------------
+    uint32_t nItems = 0;
+    if(tid < LL_CHUNK && base + tid < listEnd)
+    {
+      const uint32_t val = p.pairTri[base + tid];
+      if(!(val & PAIR_CLIPPED))
+      {
+        const uint32_t i0 = p.indices[3 * (size_t)val], i1 = p.indices[3 * (size_t)val + 1], i2 = p.indices[3 * (size_t)val + 2];
+        nItems            = setupSlot(p.tv[i0], p.tv[i1], p.tv[i2], i0, i1, i2, 0u, p.W, p.H, tileX0, tileY0, lo, slots[tid]);
+      }
+      else if(val != PAIR_SKIP)
+      {
+        // a piece of a near-clipped triangle: its vertices come from the frame's clip table (oit_clip.cuh, k_bin_emit)
+        const uint32_t   e  = val & ~PAIR_CLIPPED;
+        const ClipEntry& ce = p.clipEntries[e];
+        nItems              = setupSlot(ce.v[0], ce.v[1], ce.v[2], e, 0u, 0u, SLOT_CLIPPED, p.W, p.H, tileX0, tileY0, lo, slots[tid]);
+      }
+      else
+      {
+        slots[tid].box  = 0u;
+        slots[tid].rcpW = 0u;
+      }
+    }
+    uint32_t total;
+    {
+      const uint32_t ex = blockExclusiveScan(nItems, scanSm, total);
+      if(tid <= LL_CHUNK)
+        itemStart[tid] = ex;  // thread LL_CHUNK holds the total (the threads behind the chunk contribute nothing)
+    }
+    __syncthreads();
+
+    for(uint32_t k0 = 0; k0 < total; k0 += LL_BATCH)
+    {
+      const uint32_t par      = parity & 1u;
+      uint32_t*      setWords = reinterpret_cast<uint32_t*>(pixSet + par * TILE_PIX);
+      uint4*         setOther = pixSet + (par ^ 1u) * TILE_PIX;
+      uint32_t*      list     = lists + par * LL_BATCH;
+
+      // ---- A: coverage of LL_IPT consecutive candidates of one triangle; compact list of the covered ones --------------------
+      if(tid == 0)
+        sCount[par ^ 1u] = 0u;
+      uint32_t       recs[LL_IPT];
+      const uint32_t k = k0 + tid * LL_IPT;
+#pragma unroll
+      for(int j = 0; j < LL_IPT; j++)
+        recs[j] = 0u;
+      if(k < total)
+      {
+        int slot = 0;
+#pragma unroll
+        for(int step = LL_CHUNK / 2; step; step >>= 1)
+          if(itemStart[slot + step] <= k)
+            slot += step;
+        const TriSlot& s      = slots[slot];
+        const uint32_t bw     = ((s.box >> 8) & 15u) + 1u, bh = ((s.box >> 12) & 15u) + 1u;
+        const uint32_t local0 = k - itemStart[slot];
+#pragma unroll
+        for(int j = 0; j < LL_IPT; j++)
+        {
+          const uint32_t local = local0 + j;
+          if(local < bw * bh)
+          {
+            const uint32_t row  = (local * s.rcpW) >> 16;
+            const int      lx   = (int)((s.box & 15u) + (local - row * bw));
+            const int      ly   = (int)(((s.box >> 4) & 15u) + row);
+            const float*   dpx  = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
+            const uint32_t mask = coverageMask<S>(s, tileX0 + lx, tileY0 + ly, dpx);
+            if(mask)
+            {
+              recs[j] = (uint32_t)slot | ((uint32_t)lx << 8) | ((uint32_t)ly << 12) | (mask << 16);
+              atomicOr(&setWords[(ly * TILE_W + lx) * 4 + (slot >> 5)], 1u << (slot & 31));
+            }
+          }
+        }
+      }
+      {
+        uint32_t cnt = 0;
+#pragma unroll
+        for(int j = 0; j < LL_IPT; j++)
+          cnt += recs[j] ? 1u : 0u;
+        const uint32_t incl  = warpInclusiveScan(cnt);
+        const uint32_t wtot  = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t       wbase = 0;
+        if(lane == 31 && wtot)
+          wbase = atomicAdd(&sCount[par], wtot);
+        wbase        = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t pos = wbase + incl - cnt;
+#pragma unroll
+        for(int j = 0; j < LL_IPT; j++)
+          if(recs[j])
+            list[pos++] = recs[j];
+      }
+      __syncthreads();  // (1)
+
+      // ---- B: thread = pixel.  Fragment count of the pixel, its node range, the new head -------------------------------------
+      const uint32_t n = sCount[par];
+      if(tid == 0)
+        sBase = n ? atomicAdd(p.counter, n) : 0u;  // imageAtomicAdd(imgCounter, 1) of every fragment of the batch, at once
+      setOther[tid]     = make_uint4(0u, 0u, 0u, 0u);  // the next batch's sets (their last readers are past barrier 1)
+      const uint4    m  = pixSet[par * TILE_PIX + tid];
+      const uint32_t c0 = __popc(m.x), c1 = __popc(m.y), c2 = __popc(m.z), c3 = __popc(m.w);
+      const uint32_t c  = c0 + c1 + c2 + c3;
+      uint32_t       off;
+      {
+        const uint32_t incl = warpInclusiveScan(c);
+        if(lane == 31)
+          warpTot[warp] = incl;
+        __syncthreads();  // (2)
+        uint32_t wb = 0;
+#pragma unroll
+        for(int v = 0; v < RASTER_THREADS / 32 - 1; v++)
+          wb += v < warp ? warpTot[v] : 0u;
+        off = wb + incl - c;
+      }
+      const uint32_t nodeBase = sBase;
+      // nodes of the batch: nodeBase + 1 + q for q in [0, n) (node 0 is the list terminator); q < room fit the pool
+      const uint32_t room = nodeBase + 1u < p.capacity ? p.capacity - (nodeBase + 1u) : 0u;
+      if(c)
+      {
+        pixOff[tid]           = off;
+        pixPre[tid]           = (c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24);
+        prevHead[tid]         = headSm[tid];
+        const uint32_t stored = off < room ? min(c, room - off) : 0u;
+        if(stored)
+          headSm[tid] = nodeBase + off + stored;  // the pixel's last stored fragment
+      }
+      __syncthreads();  // (3)
+
+      // rank of a fragment among its pixel's fragments of this batch = position of its node inside the pixel's range
+      auto queuePos = [&](uint32_t rec, uint32_t& rank) {
+        const uint32_t slot = rec & (LL_CHUNK - 1), pl = (rec >> 8) & 255u, w = slot >> 5;
+        rank                = __popc(setWords[pl * 4 + w] & ((1u << (slot & 31u)) - 1u)) + ((pixPre[pl] >> (8u * w)) & 255u);
+        return pixOff[pl] + rank;
+      };
+
+      if(n <= room)
+      {
+        // ---- C: shade + store, dense and in any order ------------------------------------------------------------------------
+        for(uint32_t i = tid; i < n; i += RASTER_THREADS)
+        {
+          const uint32_t rec = list[i];
+          uint32_t       rank;
+          const uint32_t q    = queuePos(rec, rank);
+          const uint32_t node = nodeBase + 1u + q;
+          const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
+          Color4         rgba;
+          float          z;
+          shadeRecord(rec, rgba, z);
+          nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
+        }
+        nFrag += (n > (uint32_t)tid) ? (n - tid + RASTER_THREADS - 1) / RASTER_THREADS : 0u;
+        nStored += (n > (uint32_t)tid) ? (n - tid + RASTER_THREADS - 1) / RASTER_THREADS : 0u;
+      }
+      else
+      {
+        // ---- the pool runs out inside (or before) this batch --------------------------------------------------------------
+        // fragments that still fit are stored as above; all move to their pixel-major position in the list
+        uint32_t myRec[LL_IPT], myQ[LL_IPT];
+#pragma unroll
+        for(int it = 0; it < LL_IPT; it++)
+        {
+          const uint32_t i = tid + it * RASTER_THREADS;
+          myQ[it]          = 0xFFFFFFFFu;
+          myRec[it]        = 0u;
+          if(i < n)
+          {
+            const uint32_t rec = list[i];
+            uint32_t       rank;
+            const uint32_t q = queuePos(rec, rank);
+            myRec[it]        = rec;
+            myQ[it]          = q;
+            nFrag++;
+            if(q < room)
+            {
+              const uint32_t node = nodeBase + 1u + q;
+              const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
+              Color4         rgba;
+              float          z;
+              shadeRecord(rec, rgba, z);
+              nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
+              nStored++;
+            }
+            else if(p.tailBlend)
+              nTail++;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for(int it = 0; it < LL_IPT; it++)
+          if(myQ[it] != 0xFFFFFFFFu)
+            list[myQ[it]] = myRec[it];
+        __syncthreads();
+        if(p.tailBlend)
+        {
+          // tail blend (oitLinkedList.frag.glsl:82-84 + BlendMode::PREMULTIPLIED): shaded densely, 256 list positions per
+          // round, into a queue that borrows the next batch's (idle, zeroed) sets; blended by the pixel's owner in order
+          float4*   queue = reinterpret_cast<float4*>(setOther);
+          uint32_t* px    = tileColor ? tileColor + tid * S : p.color + ownPix * S;
+          for(uint32_t r0 = min(room, n); r0 < n; r0 += RASTER_THREADS)
+          {
+            const uint32_t i = r0 + tid;
+            if(i < n)
+            {
+              const uint32_t rec = list[i];
+              Color4         rgba;
+              float          z;
+              shadeRecord(rec, rgba, z);
+              const Color4 pm = premultiply(rgba);
+              queue[tid]      = make_float4(pm.r, pm.g, pm.b, pm.a);
+              tailMask[tid]   = (uint8_t)((rec >> 16) & 255u);
+            }
+            __syncthreads();
+            if(c)
+            {
+              const uint32_t qa = max(off, r0), qb = min(off + c, min(r0 + RASTER_THREADS, n));
+              for(uint32_t q = qa; q < qb; q++)
+              {
+                const float4 v = queue[q - r0];
+                const Color4 src{v.x, v.y, v.z, v.w};
+                if(!isZero(src))
+                  ropSamplesNonZero<S>(tabs, px, tailMask[q - r0], src);
+              }
+            }
+            __syncthreads();
+          }
+          setOther[tid] = make_uint4(0u, 0u, 0u, 0u);
+          __syncthreads();
+        }
+      }
+      parity++;
+    }
+    __syncthreads();  // the slots are about to be replaced
+  }
+
+  // the heads go to imgAux (the staged composite, dumps and a later colour pass read them there)
+  if(!emptyTile && ownValid)
+    p.aux[ownPix] = headSm[tid];
+
+  // ---- fused frame: composite + resolve of the tile while its nodes are still in L1 / L2 ------------------------------------
+  if(fused)
+  {
+    if(!emptyTile)
+    {
+      FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
+      __threadfence_block();
+      __syncthreads();
+      if(ownValid)
+      {
+        const AbufView av{p.abuf, headSm, (size_t)TILE_PIX};
+        fusedCompositePixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)tid, ownPix, tileColorSm + tid * S);
+      }
+    }
+    __syncthreads();
+    fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
+  }
+
+  // ---- statistics ----------------------------------------------------------------------------------------------------
+  uint32_t vals[3] = {nFrag, nStored, nTail};
+#pragma unroll
+  for(int q = 0; q < 3; q++)
+  {
+    uint32_t v = vals[q];
+#pragma unroll
+    for(int d = 16; d; d >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, d);
+    if(lane == 0 && v)
+      atomicAdd(&p.stats[q == 0 ? STAT_FRAGMENTS : (q == 1 ? STAT_STORED : STAT_TAIL)], (unsigned long long)v);
+  }
+}
+
+// The linked-list colour pass without sample shading (no AA, MSAA with coverage masks, super-sampling)
+int launchRasterLinkedList(const FrameParams& p, cudaStream_t s)
+{
+  const unsigned grid = (unsigned)(p.tilesX * p.tileRowsLocal);
+  if(grid == 0)
+    return 0;
+  const size_t dyn = p.fused ? (size_t)TILE_PIX * p.msaa * sizeof(uint32_t) : 0;
+  if(p.msaa == 1)
+    k_raster_ll<1><<<grid, RASTER_THREADS, dyn, s>>>(p);
+  else if(p.msaa == 4)
+    k_raster_ll<4><<<grid, RASTER_THREADS, dyn, s>>>(p);
+  else
+    k_raster_ll<8><<<grid, RASTER_THREADS, dyn, s>>>(p);
+  return 1;
+}
+
+}  // namespace oit
