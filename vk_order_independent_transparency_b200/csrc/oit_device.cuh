@@ -11,17 +11,18 @@
 
 namespace oit {
 
-struct SrgbTables
+struct __align__(16) SrgbTables
 {
   float dec[256];  // sRGB8 code -> linear
   float thr[256];  // thr[k]: smallest linear value whose code is >= k; thr[0] = -inf
   float a255[256]; // v / 255.0f
 };
 
+// (sm must be 16-byte aligned; g is the start of a cudaMalloc allocation)
 __device__ __forceinline__ void loadTables(SrgbTables& sm, const float* __restrict__ g)
 {
-  for(int i = threadIdx.x; i < 768; i += blockDim.x)
-    reinterpret_cast<float*>(&sm)[i] = g[i];
+  for(int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(&sm)[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }

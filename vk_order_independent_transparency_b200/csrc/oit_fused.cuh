@@ -261,6 +261,21 @@ __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const 
   }
 }
 
+// one resolved pixel (gx, gy: output coordinates inside this band's rows) to m_viewportImage -- and, in split-frame mode
+// over peer memory, straight into every band's whole-frame buffer (NVLink stores)
+__device__ __forceinline__ void fusedStorePixel(const FrameParams& p, int gx, int gy, int outW, int ss, uint32_t result)
+{
+  p.fin[(size_t)gy * outW + gx] = result;
+  if(p.peers)
+  {
+    const int    stripRows = p.stripTileRows * TILE_H / ss;
+    const int    strip     = gy / stripRows;
+    const size_t o         = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (gy - strip * stripRows)) * outW + gx;
+    for(int b = 0; b < p.bandCount; b++)
+      p.peers->frame[b][o] = result;
+  }
+}
+
 // copyOffscreenToBackBuffer for the tile: box resolve of the S samples / the ss x ss block, from the shared-memory tile
 template <int S>
 __device__ __forceinline__ void fusedResolveTile(const FrameParams& p, const SrgbTables& tb, const uint32_t* tileColor, int tileX0, int yLocal0,
@@ -276,9 +291,33 @@ __device__ __forceinline__ void fusedResolveTile(const FrameParams& p, const Srg
     if(gx >= outW || gy >= p.localH / ss)
       continue;
     uint32_t result;
+    // every sample of the block holds the same code (nothing but full-coverage blends touched the pixel: the common case):
+    // the box filter of identical values is that value -- encode(decode(v) * (1 +- 1e-6)) == v for every 8-bit v, the
+    // thresholds sit half a code away -- so the S decodes and the encode are skipped
+    bool uniform = true;
     if(S == 1 && ss == 1)
       result = tileColor[oy * TILE_W + ox];
     else
+    {
+      result = tileColor[((oy * ss) * TILE_W + ox * ss) * S];
+      for(int dy = 0; dy < ss; dy++)
+        for(int dx = 0; dx < ss; dx++)
+        {
+          const uint32_t* px = tileColor + ((oy * ss + dy) * TILE_W + (ox * ss + dx)) * S;
+          if(S % 4 == 0)
+          {
+#pragma unroll
+            for(int s4 = 0; s4 < S / 4; s4++)
+            {
+              const uint4 v = reinterpret_cast<const uint4*>(px)[s4];
+              uniform       = uniform && v.x == result && v.y == result && v.z == result && v.w == result;
+            }
+          }
+          else
+            uniform = uniform && px[0] == result;
+        }
+    }
+    if(!uniform)
     {
       float sum[4] = {0.f, 0.f, 0.f, 0.f};
       for(int dy = 0; dy < ss; dy++)
@@ -298,16 +337,22 @@ __device__ __forceinline__ void fusedResolveTile(const FrameParams& p, const Srg
       const float inv = 1.0f / (float)(ss * ss * S);
       result = encodeDst(tb, Color4{__fmul_rn(sum[0], inv), __fmul_rn(sum[1], inv), __fmul_rn(sum[2], inv), __fmul_rn(sum[3], inv)});
     }
-    p.fin[(size_t)gy * outW + gx] = result;
-    if(p.peers)
-    {
-      // split frame over peer memory: the pixel goes straight into every band's whole-frame buffer (NVLink stores)
-      const int    stripRows = p.stripTileRows * TILE_H / ss;
-      const int    strip     = gy / stripRows;
-      const size_t o         = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (gy - strip * stripRows)) * outW + gx;
-      for(int b = 0; b < p.bandCount; b++)
-        p.peers->frame[b][o] = result;
-    }
+    fusedStorePixel(p, gx, gy, outW, ss, result);
+  }
+}
+
+// a tile nothing was drawn into (and no opaque pass ran): every sample holds the clear colour, which resolves to itself
+__device__ __forceinline__ void fusedClearTile(const FrameParams& p, int tileX0, int yLocal0, int tid)
+{
+  const int ss   = p.supersample;
+  const int outW = p.W / ss;
+  const int side = TILE_W / ss;
+  for(int o = tid; o < side * side; o += blockDim.x)
+  {
+    const int oy = o / side, ox = o - oy * side;
+    const int gx = tileX0 / ss + ox, gy = yLocal0 / ss + oy;
+    if(gx < outW && gy < p.localH / ss)
+      fusedStorePixel(p, gx, gy, outW, ss, p.clearColor);
   }
 }
 

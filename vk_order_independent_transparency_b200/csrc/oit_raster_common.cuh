@@ -123,6 +123,25 @@ __device__ OIT_COLD uint32_t depthTestMask(const TriSlot& s, int ox, int oy, con
   return mask;
 }
 
+// Coverage mask of one pixel from the three edge functions e[] at the pixel's origin (fill-rule bias included) and the
+// packed edge deltas pk[] = dx | -dy << 16 of a SMALL triangle: one IDP.2A per edge and sample evaluates
+// e + dx * sy - dy * sx, the sign bits of the three are collected with one LOP3 + one funnel shift per sample.
+template <int S>
+__device__ __forceinline__ uint32_t sampleMaskSmall(const int e[3], const int pk[3])
+{
+  uint32_t outside = 0u;  // bit s: sample s fails an edge
+#pragma unroll
+  for(int sI = S - 1; sI >= 0; sI--)
+  {
+    const uint32_t sp = (uint32_t)SamplePattern<S>::y(sI) | ((uint32_t)SamplePattern<S>::x(sI) << 8);
+    const int      e0 = dp2aS16U8(pk[0], sp, e[0]);
+    const int      e1 = dp2aS16U8(pk[1], sp, e[1]);
+    const int      e2 = dp2aS16U8(pk[2], sp, e[2]);
+    outside           = __funnelshift_l((uint32_t)(e0 | e1 | e2), outside, 1);  // (outside << 1) | sign
+  }
+  return ~outside & ((1u << S) - 1u);
+}
+
 template <int S>
 __device__ __forceinline__ uint32_t coverageMask(const TriSlot& s, int gx, int gy, const float* dpx)
 {

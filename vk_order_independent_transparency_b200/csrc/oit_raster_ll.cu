@@ -80,14 +80,29 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
   const bool emptyTile  = listBegin == listEnd;
   if(fused)
   {
-    // the tile's colour samples start as the cleared (or opaque-drawn) m_colorImage content
-    for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
+    if(p.depth == nullptr)
     {
-      const int pl = i / S, gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
-      uint32_t  v  = p.clearColor;
-      if(p.depth != nullptr && gx < p.W && tileY0 + ly < p.H)
-        v = p.color[((size_t)(yLocal0 + ly) * p.W + gx) * S + (i - pl * S)];
-      tileColorSm[i] = v;
+      // no opaque pass: the tile's colour samples start as the clear colour -- and stay that if nothing is drawn into it
+      if(emptyTile)
+      {
+        fusedClearTile(p, tileX0, yLocal0, tid);
+        return;
+      }
+      const uint4 cc = make_uint4(p.clearColor, p.clearColor, p.clearColor, p.clearColor);
+      for(int i = tid; i < TILE_PIX * S / 4; i += RASTER_THREADS)
+        reinterpret_cast<uint4*>(tileColorSm)[i] = cc;
+    }
+    else
+    {
+      // ... or as what the opaque pass left in m_colorImage
+      for(int i = tid; i < TILE_PIX * S; i += RASTER_THREADS)
+      {
+        const int pl = i / S, gx = tileX0 + (pl & (TILE_W - 1)), ly = pl >> TILE_SHIFT;
+        uint32_t  v  = p.clearColor;
+        if(gx < p.W && tileY0 + ly < p.H)
+          v = p.color[((size_t)(yLocal0 + ly) * p.W + gx) * S + (i - pl * S)];
+        tileColorSm[i] = v;
+      }
     }
   }
   loadTables(tabs, p.tables);
@@ -173,26 +188,88 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
           if(itemStart[slot + step] <= k)
             slot += step;
         const TriSlot& s      = slots[slot];
-        const uint32_t bw     = ((s.box >> 8) & 15u) + 1u, bh = ((s.box >> 12) & 15u) + 1u;
+        const uint32_t box    = s.box;
+        const uint32_t bw     = ((box >> 8) & 15u) + 1u, nPix = bw * (((box >> 12) & 15u) + 1u);
         const uint32_t local0 = k - itemStart[slot];
-#pragma unroll
-        for(int j = 0; j < LL_IPT; j++)
+        uint32_t       row    = (local0 * s.rcpW) >> 16, col = local0 - row * bw;
+        // all the masks first, the shared-memory atomics afterwards: nothing in between forces the slot to be read again
+        uint32_t masks[LL_IPT], pls[LL_IPT];
+        if(box & (1u << 20))
         {
-          const uint32_t local = local0 + j;
-          if(local < bw * bh)
+          // extent <= 64 px: int32 edge functions, stepped from candidate to candidate (+1 px in x, or to the next box row)
+          int e[3], pk[3];
           {
-            const uint32_t row  = (local * s.rcpW) >> 16;
-            const int      lx   = (int)((s.box & 15u) + (local - row * bw));
-            const int      ly   = (int)(((s.box >> 4) & 15u) + row);
-            const float*   dpx  = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
-            const uint32_t mask = coverageMask<S>(s, tileX0 + lx, tileY0 + ly, dpx);
-            if(mask)
+            const int ox = (tileX0 + (int)(box & 15u) + (int)col) << 8, oy = (tileY0 + (int)((box >> 4) & 15u) + (int)row) << 8;
+#pragma unroll
+            for(int q = 0; q < 3; q++)
             {
-              recs[j] = (uint32_t)slot | ((uint32_t)lx << 8) | ((uint32_t)ly << 12) | (mask << 16);
-              atomicOr(&setWords[(ly * TILE_W + lx) * 4 + (slot >> 5)], 1u << (slot & 31));
+              const int a = (q + 1) % 3, b = (q + 2) % 3;
+              const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
+              pk[q]       = (int)(((uint32_t)dx & 0xFFFFu) | ((uint32_t)(-dy) << 16));
+              e[q]        = dx * (oy - s.y[a]) - dy * (ox - s.x[a]) - (int)((box >> (16 + q)) & 1u);
+            }
+          }
+#pragma unroll
+          for(int j = 0; j < LL_IPT; j++)
+          {
+            pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
+            masks[j] = 0u;
+            if(local0 + j < nPix)
+              masks[j] = sampleMaskSmall<S>(e, pk);
+            if(j + 1 < LL_IPT)
+            {
+              col++;
+              const bool wrap = col == bw;
+#pragma unroll
+              for(int q = 0; q < 3; q++)
+              {
+                const int ndy = pk[q] >> 16, dx = (int)(short)(pk[q] & 0xFFFF);
+                e[q] += wrap ? (dx << 8) - (ndy << 8) * (int)(bw - 1u) : (ndy << 8);
+              }
+              if(wrap)
+              {
+                col = 0u;
+                row++;
+              }
             }
           }
         }
+        else
+        {
+          // a triangle larger than 64 px: 64-bit edge functions, out of line (rare)
+#pragma unroll
+          for(int j = 0; j < LL_IPT; j++)
+          {
+            pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
+            masks[j] = 0u;
+            if(local0 + j < nPix)
+              masks[j] = coverageMaskLarge<S>(s, (tileX0 + (int)(pls[j] & 15u)) << 8, (tileY0 + (int)(pls[j] >> 4)) << 8);
+            if(++col == bw)
+            {
+              col = 0u;
+              row++;
+            }
+          }
+        }
+        if(p.depth != nullptr || !((box >> 19) & 1u))
+        {
+          // early per-sample depth test against the opaque pass (or a vertex depth close to the clear value): out of line
+#pragma unroll
+          for(int j = 0; j < LL_IPT; j++)
+            if(masks[j])
+            {
+              const int    lx = (int)(pls[j] & 15u), ly = (int)(pls[j] >> 4);
+              const float* dpx = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
+              masks[j]         = depthTestMask<S>(s, (tileX0 + lx) << 8, (tileY0 + ly) << 8, dpx, masks[j]);
+            }
+        }
+#pragma unroll
+        for(int j = 0; j < LL_IPT; j++)
+          if(masks[j])
+          {
+            recs[j] = (uint32_t)slot | (pls[j] << 8) | (masks[j] << 16);
+            atomicOr(&setWords[pls[j] * 4 + (slot >> 5)], 1u << (slot & 31));
+          }
       }
       {
         uint32_t cnt = 0;
