@@ -54,6 +54,7 @@ enum EventId
   EV_COLOR,
   EV_COMPOSITE,
   EV_RESOLVE,
+  EV_RASTER_START,  // pipelined frames: the raster half starts here (the geometry half of the NEXT frame may overlap it)
   NUM_EVENTS
 };
 }  // namespace
@@ -75,25 +76,37 @@ struct OitCtx
   OitSceneData ubo{};
   bool         haveUbo = false;
   // buffers
-  DevBuf abuf, aux, spin, adepth, counter, color, depth, wacc, wrev, fin, tables, stats;
+  DevBuf abuf, aux, spin, adepth, counter, color, depth, wacc, wrev, fin, tables;
+  // Frame pipeline: everything the GEOMETRY half of a frame produces (post-transform vertices, tile lists, clip table, the
+  // per-frame UBO copy, the statistics block) exists twice.  oit_render alternates between the two sets and issues the
+  // geometry half on its own high-priority stream, so that the vertex stage + binning of frame n+1 run while the raster
+  // half of frame n still occupies the SMs (what a GPU's geometry and pixel pipelines do across draws).
+  DevBuf       stats[2], tv[2], uboDev[2];
+  int          par       = 0;      // the set the next / current frame uses
+  bool         pipelined = true;   // OIT_B200_NO_PIPELINE=1: one set, one stream
+  cudaStream_t geoStream = nullptr;
+  cudaEvent_t  evGeoDone[2]{}, evRasterDone[2]{};
+  bool         rasterRecorded[2]{};
   // scene
-  DevBuf   verts, indices, tv;
+  DevBuf   verts, indices;
   bool     sceneOwned = false;
   uint32_t nVerts = 0, nIndices = 0, idxPerObj = 0;
   // binning (0 = transparent draw, 1 = opaque draw)
-  BinBuffers bins[2]{};
+  BinBuffers bins[2][2]{};  // [set][draw]
   uint32_t   pairTotal[2]{};
   uint32_t   drawTris[2]{};
   // per-frame UBO in device memory + its pinned staging copy; the captured frame graph
-  DevBuf          uboDev;
   DeviceUbo*      hostUbo    = nullptr;  // pinned staging ring of UBO_RING entries (frames may be in flight)
   cudaEvent_t     uboEv[UBO_RING]{};     // recorded after the upload out of slot i
   int             uboSlot      = 0;
   bool            framePending = false;  // oit_render enqueued a frame whose overflow check has not run yet
   bool            asyncRender  = true;   // oit_render returns once the frame is enqueued (OIT_B200_SYNC_RENDER=1: waits)
-  cudaGraph_t     graph      = nullptr;
-  cudaGraphExec_t graphExec  = nullptr;
+  // the captured frame, per set: [set][0] = geometry half (pipelined mode only), [set][1] = raster half / the whole frame
+  cudaGraph_t     graph[2][2]{};
+  cudaGraphExec_t graphExec[2][2]{};
   bool            graphValid = false;
+  bool            graphBuilt[2]{};
+  uint64_t        graphLaunchCount[2]{};
   bool            useGraph   = true;
   bool            capturing  = false;  // a frame is being issued without host synchronisation
   bool            fuseFrame  = false;  // oit_render: colour pass + composite + resolve in one kernel
@@ -112,8 +125,7 @@ struct OitCtx
   PeerState* peers     = nullptr;
   bool       peersOpen = false;
   bool       peersUnmapped = false;  // oit_band_peer_disable has run once: the second call frees the exported buffer
-  uint64_t        graphLaunches = 0;
-  int        sortedBuf[2]{};
+  int        sortedBuf[2][2]{};  // [set][draw]
   uint32_t*  hostScalar = nullptr;  // pinned
   OitStats   lastStats{};
   uint64_t   launches = 0;

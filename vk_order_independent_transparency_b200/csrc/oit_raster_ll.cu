@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
         if(box & (1u << 20))
         {
           // extent <= 64 px: int32 edge functions, stepped from candidate to candidate (+1 px in x, or to the next box row)
-          int e[3], pk[3];
+          int e[3], pk[3], stepX[3], stepRow[3];  // stepX: one pixel to the right; stepRow: to the first pixel of the next box row
           {
             const int ox = (tileX0 + (int)(box & 15u) + (int)col) << 8, oy = (tileY0 + (int)((box >> 4) & 15u) + (int)row) << 8;
 #pragma unroll
@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
               const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
               pk[q]       = (int)(((uint32_t)dx & 0xFFFFu) | ((uint32_t)(-dy) << 16));
               e[q]        = dx * (oy - s.y[a]) - dy * (ox - s.x[a]) - (int)((box >> (16 + q)) & 1u);
+              stepX[q]    = -(dy << 8);
+              stepRow[q]  = (dx << 8) + (dy << 8) * (int)(bw - 1u);
             }
           }
 #pragma unroll
@@ -222,10 +224,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
               const bool wrap = col == bw;
 #pragma unroll
               for(int q = 0; q < 3; q++)
-              {
-                const int ndy = pk[q] >> 16, dx = (int)(short)(pk[q] & 0xFFFF);
-                e[q] += wrap ? (dx << 8) - (ndy << 8) * (int)(bw - 1u) : (ndy << 8);
-              }
+                e[q] += wrap ? stepRow[q] : stepX[q];
               if(wrap)
               {
                 col = 0u;
@@ -346,47 +345,39 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
           shadeRecord(rec, rgba, z);
           nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
         }
-        nFrag += (n > (uint32_t)tid) ? (n - tid + RASTER_THREADS - 1) / RASTER_THREADS : 0u;
-        nStored += (n > (uint32_t)tid) ? (n - tid + RASTER_THREADS - 1) / RASTER_THREADS : 0u;
+        if(tid == 0)
+        {
+          nFrag += n;  // (the statistics are summed over the CTA at the end: one thread counts the whole batch)
+          nStored += n;
+        }
       }
       else
       {
         // ---- the pool runs out inside (or before) this batch --------------------------------------------------------------
-        // fragments that still fit are stored as above; all move to their pixel-major position in the list
-        uint32_t myRec[LL_IPT], myQ[LL_IPT];
-#pragma unroll
-        for(int it = 0; it < LL_IPT; it++)
+        // fragments that still fit are stored as above; all are copied to their pixel-major position (into the other
+        // batch's list buffer: idle until the next batch's phase A)
+        uint32_t* sorted = lists + (par ^ 1u) * LL_BATCH;
+#pragma unroll 1
+        for(uint32_t i = tid; i < n; i += RASTER_THREADS)
         {
-          const uint32_t i = tid + it * RASTER_THREADS;
-          myQ[it]          = 0xFFFFFFFFu;
-          myRec[it]        = 0u;
-          if(i < n)
+          const uint32_t rec = list[i];
+          uint32_t       rank;
+          const uint32_t q = queuePos(rec, rank);
+          sorted[q]        = rec;
+          nFrag++;
+          if(q < room)
           {
-            const uint32_t rec = list[i];
-            uint32_t       rank;
-            const uint32_t q = queuePos(rec, rank);
-            myRec[it]        = rec;
-            myQ[it]          = q;
-            nFrag++;
-            if(q < room)
-            {
-              const uint32_t node = nodeBase + 1u + q;
-              const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
-              Color4         rgba;
-              float          z;
-              shadeRecord(rec, rgba, z);
-              nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
-              nStored++;
-            }
-            else if(p.tailBlend)
-              nTail++;
+            const uint32_t node = nodeBase + 1u + q;
+            const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
+            Color4         rgba;
+            float          z;
+            shadeRecord(rec, rgba, z);
+            nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
+            nStored++;
           }
+          else if(p.tailBlend)
+            nTail++;
         }
-        __syncthreads();
-#pragma unroll
-        for(int it = 0; it < LL_IPT; it++)
-          if(myQ[it] != 0xFFFFFFFFu)
-            list[myQ[it]] = myRec[it];
         __syncthreads();
         if(p.tailBlend)
         {
@@ -399,7 +390,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
             const uint32_t i = r0 + tid;
             if(i < n)
             {
-              const uint32_t rec = list[i];
+              const uint32_t rec = sorted[i];
               Color4         rgba;
               float          z;
               shadeRecord(rec, rgba, z);
