@@ -263,13 +263,14 @@ def test_reuse_and_idempotence(oit_mod, oracle_mod):
     s.close()
 
 
-@pytest.mark.parametrize("mode", ["onchip_all", "no_onchip", "no_fuse", "no_graph", "sync_render"])
+@pytest.mark.parametrize("mode", ["onchip_all", "no_onchip", "no_fuse", "no_graph", "sync_render", "no_pipeline", "layered_ll"])
 @pytest.mark.parametrize("alg,aa,L", [(0, 0, 8), (0, 1, 4), (3, 0, 8), (3, 4, 2), (4, 1, 8), (5, 0, 8), (5, 4, 4), (6, 4, 8), (1, 1, 8)])
 def test_frame_path_variants(oit_mod, oracle_mod, monkeypatch, mode, alg, aa, L):
     """Every way oit_render can execute a frame gives the oracle's image: k-buffer slice in shared memory for all
     techniques that support it, in HBM for all, staged (unfused) kernels, and plain stream launches instead of the graph."""
     monkeypatch.setenv({"onchip_all": "OIT_B200_ONCHIP_ALL", "no_onchip": "OIT_B200_NO_ONCHIP", "no_fuse": "OIT_B200_NO_FUSE",
-                        "no_graph": "OIT_B200_NO_GRAPH", "sync_render": "OIT_B200_SYNC_RENDER"}[mode], "1")
+                        "no_graph": "OIT_B200_NO_GRAPH", "sync_render": "OIT_B200_SYNC_RENDER", "no_pipeline": "OIT_B200_NO_PIPELINE",
+                        "layered_ll": "OIT_B200_LAYERED_LL"}[mode], "1")
     s, o = run_pair(oit_mod, oracle_mod, 176, 120, algorithm=alg, aaType=aa, oitLayers=L, numObjects=180, subdiv=7)
     assert_frames_equal(s, o)
     s.close()
@@ -304,6 +305,32 @@ def test_frames_in_flight(oit_mod, alg, aa):
     assert np.array_equal(s.readColor(), got)
     s.close()
     r.close()
+
+
+@pytest.mark.parametrize("mode", ["graph", "no_graph"])
+@pytest.mark.parametrize("alg,aa", [(1, 1), (4, 2), (2, 0)])
+def test_pipelined_frames_alternate_buffer_sets(oit_mod, oracle_mod, monkeypatch, mode, alg, aa):
+    """oit_render alternates between two sets of geometry buffers and runs a frame's vertex stage + binning on its own
+    stream while the previous frame rasterises: EVERY frame of a sequence with changing cameras (some completed and read
+    back, some left in flight) must be the oracle's frame of its own camera."""
+    if mode == "no_graph":
+        monkeypatch.setenv("OIT_B200_NO_GRAPH", "1")
+    st, verts, idx, ipo = scene_for(oit_mod, algorithm=alg, aaType=aa, numObjects=150, subdiv=7)
+    W, H = 208, 144
+    cams = [oit_mod.default_camera(W, H, eye=(0.4 * i - 1.0, 0.15 * i, 11.0 + 0.3 * i)) for i in range(6)]
+    s = oit_mod.Sample(st, W, H)
+    s.setScene(verts, idx, ipo)
+    for i, cam in enumerate(cams):
+        s.onRender(cam)
+        if i in (1, 3):
+            continue   # left in flight: the next frame's geometry half overlaps this frame
+        got, gs = s.readColor().copy(), s.stats()
+        o, sd = make_oracle(oracle_mod, st, W, H, verts, idx, ipo, cam)
+        o.render(sd)
+        assert gs["fragments"] == o.stats["fragments"]
+        assert np.array_equal(got, o.final), f"frame {i}: {(got != o.final).sum()} pixels differ"
+        o.close()
+    s.close()
 
 
 def test_error_paths(oit_mod):

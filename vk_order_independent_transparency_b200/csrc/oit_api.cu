@@ -85,8 +85,10 @@ struct OitCtx
   int          par       = 0;      // the set the next / current frame uses
   bool         pipelined = true;   // OIT_B200_NO_PIPELINE=1: one set, one stream
   cudaStream_t geoStream = nullptr;
-  cudaEvent_t  evGeoDone[2]{}, evRasterDone[2]{};
+  cudaEvent_t  evGeoDone[2]{}, evRasterDone[2]{}, evMain = nullptr;
   bool         rasterRecorded[2]{};
+  bool         mainDirty = false;  // work was put on the main stream outside oit_render (scene upload, stage-by-stage calls):
+                                   // the next geometry half must not overtake it
   // scene
   DevBuf   verts, indices;
   bool     sceneOwned = false;
@@ -171,6 +173,23 @@ void devFree(DevBuf& b)
   b.bytes = 0;
 }
 
+void destroyGraphs(OitCtx* c)
+{
+  for(int set = 0; set < 2; set++)
+  {
+    for(int half = 0; half < 2; half++)
+    {
+      if(c->graphExec[set][half])
+        cudaGraphExecDestroy(c->graphExec[set][half]);
+      if(c->graph[set][half])
+        cudaGraphDestroy(c->graph[set][half]);
+      c->graphExec[set][half] = nullptr;
+      c->graph[set][half]     = nullptr;
+    }
+    c->graphBuilt[set] = false;
+  }
+}
+
 void freeBins(BinBuffers& b)
 {
   cudaFree(b.counts);
@@ -223,18 +242,30 @@ void splitObjects(const OitCtx* c, uint32_t& numTransparent, uint32_t& numOpaque
   numOpaque            = (uint32_t)(numObjects - nt);
 }
 
-void record(OitCtx* c, int id)
+void record(OitCtx* c, int id, cudaStream_t stream = nullptr)
 {
   // inside a stream capture the stage events become EXTERNAL event-record nodes, so that they are re-recorded by every
   // replay of the frame graph and cudaEventElapsedTime keeps working on them
+  if(!stream)
+    stream = c->stream;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(c->stream, &st);
+  cudaStreamIsCapturing(stream, &st);
   if(st == cudaStreamCaptureStatusActive)
-    cudaEventRecordWithFlags(c->ev[id], c->stream, cudaEventRecordExternal);
+    cudaEventRecordWithFlags(c->ev[id], stream, cudaEventRecordExternal);
   else
-    cudaEventRecord(c->ev[id], c->stream);
+    cudaEventRecord(c->ev[id], stream);
   c->evRecorded[id] = true;
 }
+
+// points the frame parameters at buffer set `par` (see OitCtx::stats)
+void selectSet(OitCtx* c, int par)
+{
+  c->par      = par;
+  c->fp.stats = (unsigned long long*)c->stats[par].p;
+  c->fp.tv    = (TVert*)c->tv[par].p;
+  c->fp.ubo   = (const DeviceUbo*)c->uboDev[par].p;
+}
+int numSets(const OitCtx* c) { return c->pipelined ? 2 : 1; }
 
 DevBuf* bufferOf(OitCtx* c, OitBuffer which)
 {
@@ -256,9 +287,9 @@ DevBuf* bufferOf(OitCtx* c, OitBuffer which)
 }
 
 // bins one draw range, asynchronously: the pair count stays on the device (BinBuffers::pairInfo)
-int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullBack)
+int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullBack, cudaStream_t stream)
 {
-  BinBuffers&    b         = c->bins[which];
+  BinBuffers&    b         = c->bins[c->par][which];
   const uint32_t triPerObj = c->idxPerObj / 3;
   const uint32_t firstTri = firstObj * triPerObj, triCount = numObj * triPerObj;
   c->drawTris[which]      = triCount;
@@ -266,7 +297,7 @@ int binDraw(OitCtx* c, int which, uint32_t firstObj, uint32_t numObj, bool cullB
     return OIT_OK;
   c->fp.clipEntries  = b.clipEntries;  // k_bin_emit fills the draw's clip table
   c->fp.clipCapacity = (uint32_t)b.clipCapacity;
-  c->launches += launchBin(c->fp, b, firstTri, triCount, cullBack, &c->sortedBuf[which], c->stream);
+  c->launches += launchBin(c->fp, b, firstTri, triCount, cullBack, &c->sortedBuf[c->par][which], stream);
   return OIT_OK;
 }
 
@@ -280,10 +311,10 @@ int growBinsIfNeeded(OitCtx* c, bool* grown)
   if(mirrored)
     overflow = c->hostMirror[STAT_OVERFLOW];
   else
-    CUDA_TRY(c, cudaMemcpy(&overflow, (unsigned long long*)c->stats.p + STAT_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(&overflow, (unsigned long long*)c->stats[c->par].p + STAT_OVERFLOW, sizeof(overflow), cudaMemcpyDeviceToHost));
   for(int which = 0; which < 2; which++)
   {
-    BinBuffers& b = c->bins[which];
+    BinBuffers& b = c->bins[c->par][which];
     if(!b.pairInfo || c->drawTris[which] == 0)
       continue;
     uint32_t info[4] = {0, 0, 0, 0};  // pairs present, pairs wanted, clip entries wanted
@@ -297,9 +328,13 @@ int growBinsIfNeeded(OitCtx* c, bool* grown)
       const size_t tris  = b.triCapacity;
       const size_t pairs = info[1] > b.pairCapacity ? (size_t)info[1] + info[1] / 4 + 1024 : b.pairCapacity;
       const size_t clips = info[2] > b.clipCapacity ? (size_t)info[2] + info[2] / 4 + 1024 : b.clipCapacity;
-      const int    r     = allocBins(c, b, tris, pairs, clips);
-      if(r != OIT_OK)
-        return r;
+      // both sets see the same scene: they grow together
+      for(int set = 0; set < numSets(c); set++)
+      {
+        const int r = allocBins(c, c->bins[set][which], tris, pairs, clips);
+        if(r != OIT_OK)
+          return r;
+      }
       *grown = true;
     }
   }
@@ -308,11 +343,12 @@ int growBinsIfNeeded(OitCtx* c, bool* grown)
 
 void useBins(OitCtx* c, int which)
 {
-  c->fp.pairTri   = c->bins[which].pairVal[c->sortedBuf[which]];
-  c->fp.tileStart = c->bins[which].tileStart;
-  c->fp.tileOrder = c->bins[which].tileOrder;
-  c->fp.clipEntries  = c->bins[which].clipEntries;
-  c->fp.clipCapacity = (uint32_t)c->bins[which].clipCapacity;
+  const BinBuffers& b = c->bins[c->par][which];
+  c->fp.pairTri       = b.pairVal[c->sortedBuf[c->par][which]];
+  c->fp.tileStart     = b.tileStart;
+  c->fp.tileOrder     = b.tileOrder;
+  c->fp.clipEntries   = b.clipEntries;
+  c->fp.clipCapacity  = (uint32_t)b.clipCapacity;
 }
 
 int ensureSceneBins(OitCtx* c)
@@ -321,18 +357,21 @@ int ensureSceneBins(OitCtx* c)
   splitObjects(c, nt, no);
   const size_t triPerObj = c->idxPerObj / 3;
   const size_t need[2]   = {nt * triPerObj, no * triPerObj};
-  for(int i = 0; i < 2; i++)
-  {
-    if(need[i] == 0)
-      continue;
-    if(c->bins[i].counts == nullptr || c->bins[i].triCapacity < need[i])
+  for(int set = 0; set < numSets(c); set++)
+    for(int i = 0; i < 2; i++)
     {
-      const size_t cap = std::max<size_t>(need[i] * 2, 1u << 16);
-      const int    r   = allocBins(c, c->bins[i], need[i], cap);
-      if(r != OIT_OK)
-        return r;
+      if(need[i] == 0)
+        continue;
+      BinBuffers& b = c->bins[set][i];
+      if(b.counts == nullptr || b.triCapacity < need[i])
+      {
+        // (a set that is created late starts with the capacity its twin has already grown to)
+        const size_t cap = std::max<size_t>(std::max<size_t>(need[i] * 2, 1u << 16), c->bins[set ^ 1][i].pairCapacity);
+        const int    r   = allocBins(c, b, need[i], cap, c->bins[set ^ 1][i].clipCapacity);
+        if(r != OIT_OK)
+          return r;
+      }
     }
-  }
   return OIT_OK;
 }
 
@@ -444,7 +483,20 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   } while(0)
 
   CREATE_CUDA(cudaSetDevice(cfg->device));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // the geometry stream gets the higher priority: its small kernels must find their way between the raster CTAs
+    int prLeast = 0, prGreatest = 0;
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prLeast));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&c->geoStream, cudaStreamNonBlocking, prGreatest));
+    for(int i = 0; i < 2; i++)
+    {
+      CREATE_CUDA(cudaEventCreateWithFlags(&c->evGeoDone[i], cudaEventDisableTiming));
+      CREATE_CUDA(cudaEventCreateWithFlags(&c->evRasterDone[i], cudaEventDisableTiming));
+    }
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evMain, cudaEventDisableTiming));
+    c->pipelined = getenv("OIT_B200_NO_PIPELINE") == nullptr;
+  }
   for(int i = 0; i < NUM_EVENTS; i++)
     CREATE_CUDA(cudaEventCreate(&c->ev[i]));
   CREATE_CUDA(cudaMallocHost(&c->hostScalar, 64));
@@ -536,11 +588,15 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
     CREATE_TRY(devAlloc(c, c->depth, P * c->msaa * 4));
   CREATE_TRY(devAlloc(c, c->fin, std::max<size_t>((size_t)cfg->width * c->localOutH, 1) * 4));
   CREATE_TRY(devAlloc(c, c->tables, 768 * sizeof(float)));
-  CREATE_TRY(devAlloc(c, c->stats, NUM_STAT_SLOTS * sizeof(unsigned long long)));
+  for(int set = 0; set < numSets(c); set++)
+  {
+    CREATE_TRY(devAlloc(c, c->stats[set], NUM_STAT_SLOTS * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMemset(c->stats[set].p, 0, c->stats[set].bytes));
+    CREATE_TRY(devAlloc(c, c->uboDev[set], sizeof(DeviceUbo)));
+  }
   float tables[768];
   buildTables(tables);
   CREATE_CUDA(cudaMemcpy(c->tables.p, tables, sizeof(tables), cudaMemcpyHostToDevice));
-  CREATE_CUDA(cudaMemset(c->stats.p, 0, c->stats.bytes));
   // clear colour (0.2, 0.2, 0.2, 0.2) linear -> B8G8R8A8_SRGB (oitRender.cpp:90)
   const uint32_t rgb = hostEnc8(tables, 0.2f);
   fp.clearColor      = rgb | (rgb << 8) | (rgb << 16) | ((uint32_t)rintf(0.2f * 255.0f) << 24);
@@ -556,9 +612,7 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   fp.wrev    = (uint16_t*)c->wrev.p;
   fp.fin     = (uint32_t*)c->fin.p;
   fp.tables  = (const float*)c->tables.p;
-  fp.stats   = (unsigned long long*)c->stats.p;
-  CREATE_TRY(devAlloc(c, c->uboDev, sizeof(DeviceUbo)));
-  fp.ubo = (const DeviceUbo*)c->uboDev.p;
+  selectSet(c, 0);
   *out          = c;
   return OIT_OK;
 #undef CREATE_TRY
@@ -570,15 +624,12 @@ int oit_destroy(OitCtx* c)
   if(!c)
     return OIT_OK;
   cudaSetDevice(c->cfg.device);
+  if(c->geoStream)
+    cudaStreamSynchronize(c->geoStream);
   if(c->stream)
     cudaStreamSynchronize(c->stream);
-  // the captured frame graph references the NCCL communicator: it has to go first
-  if(c->graphExec)
-    cudaGraphExecDestroy(c->graphExec);
-  if(c->graph)
-    cudaGraphDestroy(c->graph);
-  c->graphExec = nullptr;
-  c->graph     = nullptr;
+  // the captured frame graphs reference the NCCL communicator: they have to go first
+  destroyGraphs(c);
   gatherDestroy(c->gather);
   if(c->peers)
   {
@@ -588,15 +639,26 @@ int oit_destroy(OitCtx* c)
   if(!c->finOwned)
     c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
-                   &c->tables, &c->stats, &c->tv, &c->gatherBuf, &c->frame, &c->sphTable, &c->sphUnitPos, &c->sphUnitTri})
+                   &c->tables, &c->stats[0], &c->stats[1], &c->tv[0], &c->tv[1], &c->uboDev[0], &c->uboDev[1], &c->gatherBuf, &c->frame,
+                   &c->sphTable, &c->sphUnitPos, &c->sphUnitTri})
     devFree(*b);
   if(c->sceneOwned)
   {
     devFree(c->verts);
     devFree(c->indices);
   }
-  freeBins(c->bins[0]);
-  freeBins(c->bins[1]);
+  for(int set = 0; set < 2; set++)
+    for(int which = 0; which < 2; which++)
+      freeBins(c->bins[set][which]);
+  for(int i = 0; i < 2; i++)
+  {
+    if(c->evGeoDone[i])
+      cudaEventDestroy(c->evGeoDone[i]);
+    if(c->evRasterDone[i])
+      cudaEventDestroy(c->evRasterDone[i]);
+  }
+  if(c->evMain)
+    cudaEventDestroy(c->evMain);
   for(int i = 0; i < NUM_EVENTS; i++)
     if(c->ev[i])
       cudaEventDestroy(c->ev[i]);
@@ -609,11 +671,8 @@ int oit_destroy(OitCtx* c)
       cudaEventDestroy(c->uboEv[i]);
   if(c->hostMirror)
     cudaFreeHost(c->hostMirror);
-  if(c->graphExec)
-    cudaGraphExecDestroy(c->graphExec);
-  if(c->graph)
-    cudaGraphDestroy(c->graph);
-  devFree(c->uboDev);
+  if(c->geoStream)
+    cudaStreamDestroy(c->geoStream);
   if(c->stream)
     cudaStreamDestroy(c->stream);
   delete c;
@@ -651,13 +710,16 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
   c->nIndices   = nIndices;
   c->idxPerObj  = indicesPerObject;
   c->graphValid = false;
-  int r        = devAlloc(c, c->tv, (size_t)nVerts * sizeof(TVert));
-  if(r != OIT_OK)
-    return r;
+  for(int set = 0; set < numSets(c); set++)
+  {
+    const int r = devAlloc(c, c->tv[set], (size_t)nVerts * sizeof(TVert));
+    if(r != OIT_OK)
+      return r;
+  }
   c->fp.verts   = (const float*)c->verts.p;
   c->fp.indices = (const uint32_t*)c->indices.p;
-  c->fp.tv      = (TVert*)c->tv.p;
   c->fp.nVerts  = nVerts;
+  selectSet(c, c->par);
   return ensureSceneBins(c);
 }
 
@@ -665,7 +727,7 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
 // the sample's 3.1 M indices costs more than the frame).  On failure the context is left without a scene.
 static int validateIndices(OitCtx* c, const uint32_t* dIndices, uint32_t nIndices, uint32_t nVerts)
 {
-  unsigned long long* flag = (unsigned long long*)c->stats.p + STAT_SCRATCH;  // no frame is in flight here
+  unsigned long long* flag = (unsigned long long*)c->stats[0].p + STAT_SCRATCH;  // no frame is in flight here
   CUDA_TRY(c, cudaMemsetAsync(flag, 0, sizeof(*flag), c->stream));
   launchValidateIndices(dIndices, nIndices, nVerts, flag, c->stream);
   unsigned long long bad = 0;
@@ -691,6 +753,7 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
     return OIT_ERR_INVALID_ARG;
   if(!vertices || !indices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  c->mainDirty = true;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
@@ -719,7 +782,7 @@ int oit_set_scene(OitCtx* c, const void* vertices, uint32_t nVerts, const uint32
   int r = validateIndices(c, (const uint32_t*)c->indices.p, nIndices, nVerts);
   if(r != OIT_OK)
     return r;
-  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != indicesPerObject || !c->tv.p)
+  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != indicesPerObject || !c->tv[0].p)
     return installScene(c, nVerts, nIndices, indicesPerObject);
   c->fp.verts   = (const float*)c->verts.p;
   c->fp.indices = (const uint32_t*)c->indices.p;
@@ -732,6 +795,7 @@ int oit_set_scene_device(OitCtx* c, const void* dVertices, uint32_t nVerts, cons
     return OIT_ERR_INVALID_ARG;
   if(!dVertices || !dIndices || nVerts == 0 || indicesPerObject == 0 || indicesPerObject % 3 || nIndices % indicesPerObject)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  c->mainDirty = true;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
@@ -761,6 +825,7 @@ int oit_set_scene_spheres(OitCtx* c, const OitSphere* spheres, uint32_t nSpheres
   uint32_t nVerts = 0, nIndices = 0, ipo = 0;
   if(!spheres || nSpheres == 0 || nSpheres > 0x7FFFFFFFu || oit_scene_sizes(&sizes, &nVerts, &nIndices, &ipo) != OIT_OK)
     return fail(c, OIT_ERR_INVALID_ARG, "bad scene arguments");
+  c->mainDirty = true;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
@@ -801,17 +866,16 @@ int oit_set_scene_spheres(OitCtx* c, const OitSphere* spheres, uint32_t nSpheres
   launchExpandSpheres((const float*)c->sphTable.p, nSpheres, (const float*)c->sphUnitPos.p, nVerts / nSpheres, (const uint32_t*)c->sphUnitTri.p,
                       ipo, (float*)c->verts.p, (uint32_t*)c->indices.p, c->stream);
   CUDA_TRY(c, cudaGetLastError());
-  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != ipo || !c->tv.p)
+  if(c->nVerts != nVerts || c->nIndices != nIndices || c->idxPerObj != ipo || !c->tv[0].p)
     return installScene(c, nVerts, nIndices, ipo);
   c->fp.verts   = (const float*)c->verts.p;
   c->fp.indices = (const uint32_t*)c->indices.p;
   return OIT_OK;
 }
 
-int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
+// uploads the per-frame UBO into buffer set c->par, ordered on `stream`
+static int uploadSceneData(OitCtx* c, const OitSceneData* ubo, cudaStream_t stream)
 {
-  if(!c || !ubo)
-    return OIT_ERR_INVALID_ARG;
   c->ubo = *ubo;
   // updateUniformBuffer (main.cpp:628-637) + createFrameImages (oit.cpp:102-152) own these fields
   c->ubo.viewport[0] = (int32_t)c->bufW;
@@ -829,9 +893,35 @@ int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
   memcpy(slot->view, ubo->viewMatrix, sizeof(float) * 16);
   slot->alphaMin   = ubo->alphaMin;
   slot->alphaWidth = ubo->alphaWidth;
-  CUDA_TRY(c, cudaMemcpyAsync(c->uboDev.p, slot, sizeof(DeviceUbo), cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(c, cudaEventRecord(c->uboEv[c->uboSlot], c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->uboDev[c->par].p, slot, sizeof(DeviceUbo), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(c, cudaEventRecord(c->uboEv[c->uboSlot], stream));
   c->haveUbo       = true;
+  return OIT_OK;
+}
+
+int oit_set_scene_data(OitCtx* c, const OitSceneData* ubo)
+{
+  if(!c || !ubo)
+    return OIT_ERR_INVALID_ARG;
+  // (on the main stream: ordered behind every frame in flight, whose raster halves follow their geometry halves)
+  c->mainDirty = true;
+  return uploadSceneData(c, ubo, c->stream);
+}
+
+// The geometry half of a frame on `stream`: statistics reset, vertex stage, binning of both draws (into buffer set c->par)
+static int issueGeometry(OitCtx* c, cudaStream_t stream)
+{
+  record(c, EV_START, stream);
+  CUDA_TRY(c, cudaMemsetAsync(c->stats[c->par].p, 0, c->stats[c->par].bytes, stream));
+  c->launches += launchTransformVertices(c->fp, stream);
+  uint32_t nt, no;
+  splitObjects(c, nt, no);
+  int r;
+  if((r = binDraw(c, 0, 0, nt, false, stream)) != OIT_OK)
+    return r;
+  if((r = binDraw(c, 1, nt, no, true, stream)) != OIT_OK)
+    return r;
+  record(c, EV_GEOM, stream);
   return OIT_OK;
 }
 
@@ -843,45 +933,35 @@ int oit_begin_frame(OitCtx* c)
     return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
   if(!c->haveUbo)
     return fail(c, OIT_ERR_INVALID_ARG, "oit_set_scene_data has not been called");
+  c->mainDirty = c->mainDirty || !c->capturing;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->capturing && c->framePending)
     if(const int fr = finishFrame(c); fr != OIT_OK)
       return fr;
-  c->launches = 0;
-  for(bool& b : c->evRecorded)
-    b = false;
-  record(c, EV_START);
-  CUDA_TRY(c, cudaMemsetAsync(c->stats.p, 0, c->stats.bytes, c->stream));
-  // vertex stage + binning of both draws
-  c->launches += launchTransformVertices(c->fp, c->stream);
-  uint32_t nt, no;
-  splitObjects(c, nt, no);
-  int r = ensureSceneBins(c);
-  if(r != OIT_OK)
-    return r;
-  if((r = binDraw(c, 0, 0, nt, false)) != OIT_OK)
-    return r;
-  if((r = binDraw(c, 1, nt, no, true)) != OIT_OK)
-    return r;
+  int r = OIT_OK;
   if(!c->capturing)
   {
-    // stage-by-stage use: make sure the pair buffers were large enough before anything consumes the bins
-    // (oit_render does this check once per frame instead, after the whole asynchronous frame)
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    bool grown = false;
-    if((r = growBinsIfNeeded(c, &grown)) != OIT_OK)
+    // stage-by-stage use: everything on the main stream; the pair buffers must be large enough before anything consumes
+    // the bins (oit_render checks once per frame instead, after the whole asynchronous frame)
+    c->launches = 0;
+    for(bool& b : c->evRecorded)
+      b = false;
+    selectSet(c, c->par);
+    if((r = ensureSceneBins(c)) != OIT_OK)
       return r;
-    if(grown)
+    for(int attempt = 0; attempt < 4; attempt++)
     {
-      CUDA_TRY(c, cudaMemsetAsync(c->stats.p, 0, c->stats.bytes, c->stream));
-      c->launches += launchTransformVertices(c->fp, c->stream);
-      if((r = binDraw(c, 0, 0, nt, false)) != OIT_OK)
+      if((r = issueGeometry(c, c->stream)) != OIT_OK)
         return r;
-      if((r = binDraw(c, 1, nt, no, true)) != OIT_OK)
+      CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      bool grown = false;
+      if((r = growBinsIfNeeded(c, &grown)) != OIT_OK)
         return r;
+      if(!grown)
+        break;
     }
   }
-  record(c, EV_GEOM);
+  record(c, EV_RASTER_START);
   // clearTransparent* + colour/depth clear
   c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream);
   record(c, EV_CLEAR);
@@ -893,6 +973,7 @@ int oit_draw_opaque(OitCtx* c)
 {
   if(!c)
     return OIT_ERR_INVALID_ARG;
+  c->mainDirty = c->mainDirty || !c->capturing;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(c->drawTris[1] > 0 && c->fp.depth)
   {
@@ -908,6 +989,7 @@ int oit_draw_transparent(OitCtx* c)
 {
   if(!c)
     return OIT_ERR_INVALID_ARG;
+  c->mainDirty = c->mainDirty || !c->capturing;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(c->drawTris[0] > 0)
   {
@@ -935,6 +1017,7 @@ int oit_composite(OitCtx* c)
 {
   if(!c)
     return OIT_ERR_INVALID_ARG;
+  c->mainDirty = c->mainDirty || !c->capturing;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->fp.fused)
     c->launches += launchComposite(c->fp, (int)c->cfg.algorithm, c->stream);
@@ -947,6 +1030,7 @@ int oit_resolve(OitCtx* c)
 {
   if(!c)
     return OIT_ERR_INVALID_ARG;
+  c->mainDirty = c->mainDirty || !c->capturing;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->fp.fused)
     c->launches += launchResolve(c->fp, c->supersample, (int)c->cfg.width, (int)c->localOutH, c->stream);
@@ -965,22 +1049,28 @@ int oit_synchronize(OitCtx* c)
   return OIT_OK;
 }
 
-// every stage of one frame, asynchronously on the context's stream
-static int issueFrame(OitCtx* c)
+// "my frame buffer may be overwritten": the first thing a band says about a frame (split frame over peer memory)
+static void issueReadySignal(OitCtx* c)
 {
-  int        r;
-  const bool exchange = c->peers && c->peersOpen;
-  // split frame over peer memory: "my frame buffer may be overwritten" goes out first, the wait for the other bands'
-  // comes as late as possible (the geometry stage and the opaque pass absorb the skew between the bands)
-  if(exchange)
-    c->launches += peerSignal(c->peers, PEER_FLAG_READY, (const unsigned long long*)c->stats.p, c->stream);
-  if((r = oit_begin_frame(c)) != OIT_OK)
+  if(c->peers && c->peersOpen)
+    c->launches += peerSignal(c->peers, PEER_FLAG_READY, (const unsigned long long*)c->stats[c->par].p, c->stream);
+}
+
+// The raster half of one frame, asynchronously on the main stream: clears, opaque pass, colour pass(es), composite, resolve,
+// the band exchange and the statistics mirror.  Reads what the geometry half left in buffer set c->par.
+static int issueRaster(OitCtx* c)
+{
+  int                 r;
+  const bool          exchange = c->peers && c->peersOpen;
+  unsigned long long* stats    = (unsigned long long*)c->stats[c->par].p;
+  if((r = oit_begin_frame(c)) != OIT_OK)  // (c->capturing: only the clears)
     return r;
   if((r = oit_draw_opaque(c)) != OIT_OK)
     return r;
   if(exchange)
   {
-    c->launches += peerWait(c->peers, PEER_FLAG_READY, (unsigned long long*)c->stats.p, c->stream);
+    // the wait for the other bands' READY comes as late as possible: the clears and the opaque pass absorb the skew
+    c->launches += peerWait(c->peers, PEER_FLAG_READY, stats, c->stream);
     record(c, EV_OPAQUE);  // time spent waiting for the other bands is not the colour pass's
   }
   c->fp.peers = (exchange && c->fp.fused) ? peerTable(c->peers) : nullptr;  // the fused kernel stores to every band
@@ -997,29 +1087,118 @@ static int issueFrame(OitCtx* c)
     if(!c->fp.fused)
       c->launches += peerScatterRows(c->peers, (const uint32_t*)c->fin.p, (int)c->cfg.width, (int)c->localOutH, (int)c->stripRows, c->stream);
     // DONE carries this band's overflow flag: after the wait every band knows whether any band repeats the frame
-    c->launches += peerSignal(c->peers, PEER_FLAG_DONE, (const unsigned long long*)c->stats.p, c->stream);
-    c->launches += peerWait(c->peers, PEER_FLAG_DONE, (unsigned long long*)c->stats.p, c->stream);
+    c->launches += peerSignal(c->peers, PEER_FLAG_DONE, stats, c->stream);
+    c->launches += peerWait(c->peers, PEER_FLAG_DONE, stats, c->stream);
     CUDA_TRY(c, cudaGetLastError());
   }
   // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
   if(c->gather)
   {
     const int n = gatherLaunch(c->gather, (uint32_t*)c->gatherBuf.p, (uint32_t*)c->frame.p, (int)c->cfg.width, (int)c->cfg.height,
-                               (int)c->stripRows, (int)c->padRows, (unsigned long long*)c->stats.p, c->stream, c->error);
+                               (int)c->stripRows, (int)c->padRows, stats, c->stream, c->error);
     if(n < 0)
       return n;
     c->launches += n;
   }
   // mirror the statistics and the pair counts into pinned host memory as the last nodes of the frame
-  CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror, c->stats.p, NUM_STAT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror, stats, NUM_STAT_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   for(int which = 0; which < 2; which++)
-    if(c->bins[which].pairInfo && c->drawTris[which] > 0)
-      CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror + NUM_STAT_SLOTS + 2 * which, c->bins[which].pairInfo, 4 * sizeof(uint32_t),
+    if(c->bins[c->par][which].pairInfo && c->drawTris[which] > 0)
+      CUDA_TRY(c, cudaMemcpyAsync(c->hostMirror + NUM_STAT_SLOTS + 2 * which, c->bins[c->par][which].pairInfo, 4 * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, c->stream));
   return OIT_OK;
 }
 
-// Enqueues one frame on the context's stream (graph replay, or plain launches) without waiting for it.
+// One frame, stage by stage, without host synchronisation.  Pipelined: the geometry half goes to the geometry stream and
+// the raster half waits for it with an event, so that the NEXT frame's geometry half (other buffer set) overlaps this
+// frame's raster half.  Otherwise everything is issued on the main stream.
+static int issueFrameStreams(OitCtx* c)
+{
+  int r;
+  c->launches = 0;
+  for(bool& b : c->evRecorded)
+    b = false;
+  if(c->pipelined)
+  {
+    if((r = issueGeometry(c, c->geoStream)) != OIT_OK)
+      return r;
+    CUDA_TRY(c, cudaEventRecord(c->evGeoDone[c->par], c->geoStream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evGeoDone[c->par], 0));
+    issueReadySignal(c);
+    if((r = issueRaster(c)) != OIT_OK)
+      return r;
+    CUDA_TRY(c, cudaEventRecord(c->evRasterDone[c->par], c->stream));
+    c->rasterRecorded[c->par] = true;
+    return OIT_OK;
+  }
+  issueReadySignal(c);
+  if((r = issueGeometry(c, c->stream)) != OIT_OK)
+    return r;
+  return issueRaster(c);
+}
+
+// The same, captured once per buffer set and replayed: the geometry half and the raster half are separate graphs
+// (pipelined), or one graph holds the whole frame.
+static int buildGraphs(OitCtx* c)
+{
+  const int set = c->par;
+  int       r   = OIT_OK;
+  c->launches   = 0;
+  for(bool& b : c->evRecorded)
+    b = false;
+  cudaError_t e = cudaSuccess;
+  if(c->pipelined)
+  {
+    e = cudaStreamBeginCapture(c->geoStream, cudaStreamCaptureModeThreadLocal);
+    if(e == cudaSuccess)
+    {
+      r = issueGeometry(c, c->geoStream);
+      e = cudaStreamEndCapture(c->geoStream, &c->graph[set][0]);
+      if(r == OIT_OK && e == cudaSuccess)
+        e = cudaGraphInstantiate(&c->graphExec[set][0], c->graph[set][0], 0);
+    }
+    if(r != OIT_OK || e != cudaSuccess)
+      return OIT_ERR_CUDA;
+  }
+  e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+  if(e == cudaSuccess)
+  {
+    issueReadySignal(c);
+    if(!c->pipelined)
+      r = issueGeometry(c, c->stream);
+    if(r == OIT_OK)
+      r = issueRaster(c);
+    e = cudaStreamEndCapture(c->stream, &c->graph[set][1]);
+    if(r == OIT_OK && e == cudaSuccess)
+      e = cudaGraphInstantiate(&c->graphExec[set][1], c->graph[set][1], 0);
+  }
+  if(r != OIT_OK || e != cudaSuccess)
+    return OIT_ERR_CUDA;
+  c->graphBuilt[set]       = true;
+  c->graphLaunchCount[set] = c->launches;
+  return OIT_OK;
+}
+
+static int launchGraphs(OitCtx* c)
+{
+  const int set = c->par;
+  c->launches   = c->graphLaunchCount[set];
+  if(c->pipelined)
+  {
+    CUDA_TRY(c, cudaGraphLaunch(c->graphExec[set][0], c->geoStream));
+    CUDA_TRY(c, cudaEventRecord(c->evGeoDone[set], c->geoStream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evGeoDone[set], 0));
+  }
+  CUDA_TRY(c, cudaGraphLaunch(c->graphExec[set][1], c->stream));
+  if(c->pipelined)
+  {
+    CUDA_TRY(c, cudaEventRecord(c->evRasterDone[set], c->stream));
+    c->rasterRecorded[set] = true;
+  }
+  return OIT_OK;
+}
+
+// Enqueues one frame (buffer set c->par, whose UBO has been uploaded) without waiting for it.
 static int enqueueFrame(OitCtx* c)
 {
   int r = OIT_OK;
@@ -1027,6 +1206,7 @@ static int enqueueFrame(OitCtx* c)
   {
     if((r = ensureSceneBins(c)) != OIT_OK)
       return r;
+    selectSet(c, c->par);
     c->capturing = true;  // the frame is issued without host synchronisation; overflow is checked once at the end
     {
       // the fused kernel is the transparent colour pass: without transparent triangles the staged kernels resolve the frame
@@ -1047,45 +1227,24 @@ static int enqueueFrame(OitCtx* c)
     // (with the band gather, the first frame runs un-captured so that NCCL sets up its connections outside a capture)
     if(c->useGraph && (!c->gather || c->gatherWarm))
     {
-      // the whole frame (~30 kernels) is captured once and replayed as one graph launch
+      // a frame (~30 kernels) is captured once per buffer set and replayed with one or two graph launches
       if(!c->graphValid)
       {
-        if(c->graphExec)
-          cudaGraphExecDestroy(c->graphExec);
-        if(c->graph)
-          cudaGraphDestroy(c->graph);
-        c->graphExec = nullptr;
-        c->graph     = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-        if(e == cudaSuccess)
-        {
-          r = issueFrame(c);
-          e = cudaStreamEndCapture(c->stream, &c->graph);
-          if(r == OIT_OK && e == cudaSuccess)
-            e = cudaGraphInstantiate(&c->graphExec, c->graph, 0);
-        }
-        if(r != OIT_OK || e != cudaSuccess)
-        {
-          cudaGetLastError();
-          c->useGraph = false;  // fall back to plain stream launches
-          retry       = true;
-        }
-        else
-        {
-          c->graphValid    = true;
-          c->graphLaunches = c->launches;
-        }
+        destroyGraphs(c);
+        c->graphValid = true;
+      }
+      if(!c->graphBuilt[c->par] && buildGraphs(c) != OIT_OK)
+      {
+        cudaGetLastError();
+        destroyGraphs(c);
+        c->useGraph = false;  // fall back to plain stream launches
+        retry       = true;
       }
       if(!retry)
-      {
-        c->launches         = c->graphLaunches;
-        const cudaError_t e = cudaGraphLaunch(c->graphExec, c->stream);
-        if(e != cudaSuccess)
-          r = fail(c, OIT_ERR_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
-      }
+        r = launchGraphs(c);
     }
     else
-      r = issueFrame(c);
+      r = issueFrameStreams(c);
     c->capturing = false;
     c->fp.fused  = 0;
     c->fp.onChip = 0;
@@ -1103,11 +1262,14 @@ static int finishFrame(OitCtx* c)
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->framePending)
   {
+    CUDA_TRY(c, cudaStreamSynchronize(c->geoStream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return OIT_OK;
   }
   for(int attempt = 0; attempt < 4; attempt++)
   {
+    // (every raster half waits for its geometry half: the main stream drains last)
+    CUDA_TRY(c, cudaStreamSynchronize(c->geoStream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->framePending = false;
     bool grown      = false;
@@ -1142,10 +1304,11 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
   if(!c)
     return OIT_ERR_INVALID_ARG;
   int r;
-  if((r = oit_set_scene_data(c, ubo)) != OIT_OK)
-    return r;
+  if(!ubo)
+    return OIT_ERR_INVALID_ARG;
   if(!c->verts.p || !c->indices.p)
     return fail(c, OIT_ERR_NO_SCENE, "oit_set_scene has not been called");
+  CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   // a frame in flight that already reported a pair-buffer overflow (the mirror is pinned host memory written by the frame's
   // last nodes): grow the buffers now instead of letting further frames run with truncated triangle lists
   // (not in split-frame mode: there the bands must take the decision at the same frame, which finishFrame guarantees)
@@ -1153,6 +1316,26 @@ int oit_render(OitCtx* c, const OitSceneData* ubo)
      && reinterpret_cast<volatile unsigned long long*>(c->hostMirror)[STAT_OVERFLOW] != 0)
     if((r = finishFrame(c)) != OIT_OK)
       return r;
+  if(c->pipelined)
+  {
+    // the other buffer set: its geometry half may start as soon as the raster half that last read the set (two frames ago)
+    // is done -- normally long ago -- i.e. while the previous frame's raster half is still running
+    const int set = c->par ^ 1;
+    if(c->rasterRecorded[set])
+      CUDA_TRY(c, cudaStreamWaitEvent(c->geoStream, c->evRasterDone[set], 0));
+    if(c->mainDirty)
+    {
+      // a scene upload or stage-by-stage work is queued on the main stream: the geometry stream gets in line behind it
+      CUDA_TRY(c, cudaEventRecord(c->evMain, c->stream));
+      CUDA_TRY(c, cudaStreamWaitEvent(c->geoStream, c->evMain, 0));
+      c->mainDirty = false;
+    }
+    selectSet(c, set);
+    if((r = uploadSceneData(c, ubo, c->geoStream)) != OIT_OK)
+      return r;
+  }
+  else if((r = uploadSceneData(c, ubo, c->stream)) != OIT_OK)
+    return r;
   if((r = enqueueFrame(c)) != OIT_OK)
     return r;
   c->framePending = true;
@@ -1172,7 +1355,7 @@ int oit_get_stats(OitCtx* c, OitStats* out)
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
   unsigned long long h[NUM_STAT_SLOTS];
-  CUDA_TRY(c, cudaMemcpy(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+  CUDA_TRY(c, cudaMemcpy(h, c->stats[c->par].p, sizeof(h), cudaMemcpyDeviceToHost));
   OitStats s{};
   s.fragments         = h[STAT_FRAGMENTS];
   s.fragmentsStored   = h[STAT_STORED];
@@ -1198,12 +1381,13 @@ int oit_get_stats(OitCtx* c, OitStats* out)
     return 0.f;
   };
   s.msGeometry  = ms(EV_START, EV_GEOM);
-  s.msClear     = ms(EV_GEOM, EV_CLEAR);
+  s.msClear     = ms(EV_RASTER_START, EV_CLEAR);
   s.msOpaque    = ms(EV_CLEAR, EV_OPAQUE);
   s.msColor     = ms(EV_OPAQUE, EV_COLOR);
   s.msComposite = ms(EV_COLOR, EV_COMPOSITE);
   s.msResolve   = ms(EV_COMPOSITE, EV_RESOLVE);
-  s.msFrame     = ms(EV_START, EV_RESOLVE);
+  // the two halves of a frame run on two streams (the next frame's geometry overlaps this frame's raster): their sum
+  s.msFrame     = s.msGeometry + ms(EV_RASTER_START, EV_RESOLVE);
   c->lastStats  = s;
   *out          = s;
   return OIT_OK;
@@ -1246,6 +1430,7 @@ int oit_upload(OitCtx* c, OitBuffer which, const void* host, size_t bytes)
     return fail(c, OIT_ERR_INVALID_ARG, "buffer not allocated for this configuration");
   if(bytes != b->bytes)
     return fail(c, OIT_ERR_SIZE, "host size does not match the device buffer");
+  c->mainDirty = true;
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;

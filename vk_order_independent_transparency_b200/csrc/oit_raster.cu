@@ -470,8 +470,7 @@ static void launchPass(const FrameParams& p, cudaStream_t s)
 // OIT_B200_LAYERED_LL=1: the linked list through the generic primitive-ordered kernel (A/B comparisons, tests)
 static bool useLayeredLinkedList()
 {
-  static const bool v = getenv("OIT_B200_LAYERED_LL") != nullptr;
-  return v;
+  return getenv("OIT_B200_LAYERED_LL") != nullptr;  // (read when a frame is issued or captured, not per replay)
 }
 
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s)
