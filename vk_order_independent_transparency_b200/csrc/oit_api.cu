@@ -76,7 +76,7 @@ struct OitCtx
   OitSceneData ubo{};
   bool         haveUbo = false;
   // buffers
-  DevBuf abuf, aux, spin, adepth, counter, color, depth, wacc, wrev, fin, tables;
+  DevBuf abuf, aux, spin, adepth, counter, color, depth, wacc, wrev, fin, tables, rowLocal;
   // Frame pipeline: everything the GEOMETRY half of a frame produces (post-transform vertices, tile lists, clip table, the
   // per-frame UBO copy, the statistics block) exists twice.  oit_render alternates between the two sets and issues the
   // geometry half on its own high-priority stream, so that the vertex stage + binning of frame n+1 run while the raster
@@ -192,13 +192,12 @@ void destroyGraphs(OitCtx* c)
 
 void freeBins(BinBuffers& b)
 {
-  cudaFree(b.counts);
+  cudaFree(b.lb);
   cudaFree(b.pairKey[0]);
   cudaFree(b.pairKey[1]);
   cudaFree(b.pairVal[0]);
   cudaFree(b.pairVal[1]);
   cudaFree(b.tileStart);
-  cudaFree(b.pairInfo);
   cudaFree(b.clipEntries);
   cudaFree(b.scratch);
   cudaFree(b.tileOrder);
@@ -215,15 +214,16 @@ int allocBins(OitCtx* c, BinBuffers& b, size_t triCount, size_t pairCapacity, si
   b.pairCapacity = pairCapacity;
   b.triCapacity  = triCount;
   b.scratchWords = binScratchWords(triCount, pairCapacity, numTiles);
-  CUDA_TRY(c, cudaMalloc(&b.counts, (triCount + 1) * sizeof(uint32_t)));
+  b.lbBytes = binLookbackBytes(triCount, pairCapacity);
+  CUDA_TRY(c, cudaMalloc(&b.lb, b.lbBytes));
+  CUDA_TRY(c, cudaMemset(b.lb, 0, b.lbBytes));
+  b.pairInfo = b.lb;
   for(int i = 0; i < 2; i++)
   {
     CUDA_TRY(c, cudaMalloc(&b.pairKey[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
     CUDA_TRY(c, cudaMalloc(&b.pairVal[i], std::max<size_t>(pairCapacity, 1) * sizeof(uint32_t)));
   }
   CUDA_TRY(c, cudaMalloc(&b.tileStart, (numTiles + 1) * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMalloc(&b.pairInfo, 4 * sizeof(uint32_t)));
-  CUDA_TRY(c, cudaMemset(b.pairInfo, 0, 4 * sizeof(uint32_t)));
   b.clipCapacity = clipCapacity;
   CUDA_TRY(c, cudaMalloc(&b.clipEntries, clipCapacity * sizeof(ClipEntry)));
   CUDA_TRY(c, cudaMalloc(&b.tileOrder, std::max<size_t>(numTiles, 1) * sizeof(uint32_t)));
@@ -262,7 +262,8 @@ void selectSet(OitCtx* c, int par)
 {
   c->par      = par;
   c->fp.stats = (unsigned long long*)c->stats[par].p;
-  c->fp.tv    = (TVert*)c->tv[par].p;
+  c->fp.tv      = (TVert*)c->tv[par].p;
+  c->fp.tvViewz = c->tv[par].p ? (float*)((TVert*)c->tv[par].p + c->nVerts) : nullptr;
   c->fp.ubo   = (const DeviceUbo*)c->uboDev[par].p;
 }
 int numSets(const OitCtx* c) { return c->pipelined ? 2 : 1; }
@@ -363,7 +364,7 @@ int ensureSceneBins(OitCtx* c)
       if(need[i] == 0)
         continue;
       BinBuffers& b = c->bins[set][i];
-      if(b.counts == nullptr || b.triCapacity < need[i])
+      if(b.lb == nullptr || b.triCapacity < need[i])
       {
         // (a set that is created late starts with the capacity its twin has already grown to)
         const size_t cap = std::max<size_t>(std::max<size_t>(need[i] * 2, 1u << 16), c->bins[set ^ 1][i].pairCapacity);
@@ -538,6 +539,16 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
       fp.tileRowsLocal++;
       localBufH += (uint32_t)std::min(TILE_H, fp.H - R * TILE_H);
     }
+  {
+    // which global tile rows this band owns, and where they sit in its buffers (the binning looks rows up here)
+    std::vector<int32_t> rowLocal((size_t)std::max(fp.tileRowsGlobal, 1), -1);
+    for(int R = 0; R < fp.tileRowsGlobal; R++)
+      if(tileRowOwner(R, fp.stripTileRows, fp.bandCount) == fp.bandIndex)
+        rowLocal[R] = tileRowToLocal(R, fp.stripTileRows, fp.bandCount);
+    CREATE_TRY(devAlloc(c, c->rowLocal, rowLocal.size() * sizeof(int32_t)));
+    CREATE_CUDA(cudaMemcpy(c->rowLocal.p, rowLocal.data(), rowLocal.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    fp.rowLocal = (const int32_t*)c->rowLocal.p;
+  }
   c->localBufH = localBufH;
   c->localOutH = localBufH / c->supersample;
   fp.localH    = (int)localBufH;
@@ -639,7 +650,7 @@ int oit_destroy(OitCtx* c)
   if(!c->finOwned)
     c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
-                   &c->tables, &c->stats[0], &c->stats[1], &c->tv[0], &c->tv[1], &c->uboDev[0], &c->uboDev[1], &c->gatherBuf, &c->frame,
+                   &c->tables, &c->rowLocal, &c->stats[0], &c->stats[1], &c->tv[0], &c->tv[1], &c->uboDev[0], &c->uboDev[1], &c->gatherBuf, &c->frame,
                    &c->sphTable, &c->sphUnitPos, &c->sphUnitTri})
     devFree(*b);
   if(c->sceneOwned)
@@ -712,7 +723,7 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
   c->graphValid = false;
   for(int set = 0; set < numSets(c); set++)
   {
-    const int r = devAlloc(c, c->tv[set], (size_t)nVerts * sizeof(TVert));
+    const int r = devAlloc(c, c->tv[set], (size_t)nVerts * (sizeof(TVert) + sizeof(float)));  // [TVert table][view-space depths]
     if(r != OIT_OK)
       return r;
   }
@@ -1278,6 +1289,8 @@ static int finishFrame(OitCtx* c)
     c->mirrorValid  = false;
     if(r != OIT_OK)
       return r;
+    if(c->hostMirror[STAT_INTERNAL] != 0)
+      return fail(c, OIT_ERR_CUDA, "internal error: a look-back chain of the binning timed out");
     if(c->hostMirror[STAT_PEER_TIMEOUT] != 0)
       return fail(c, OIT_ERR_CUDA, "split frame: a band did not reach the frame barrier (peer exchange timed out)");
     // Split frame: the decision to render the frame again is COLLECTIVE.  The exchange itself carried every band's overflow

@@ -24,10 +24,9 @@
 namespace oit {
 
 // the vertex stage after the matrix product: perspective divide, viewport transform, guard band, snapping to 1/256 px
-__device__ __forceinline__ TVert finishVertex(const float clip[4], float viewz, float hw, float hh)
+__device__ __forceinline__ TVert finishVertex(const float clip[4], float hw, float hh)
 {
   TVert t;
-  t.viewz = viewz;
   t.x     = INT32_MIN;
   t.y     = 0;
   t.z     = 0.f;
@@ -73,6 +72,7 @@ __device__ __forceinline__ void clipSpaceVertex(const ClipInput& p, uint32_t ind
 struct ClipVert
 {
   TVert v;
+  float viewz;
   int   i, j;  // attribute source: original vertex i (t == 0), or the point t of the way from i to j
   float t;
 };
@@ -108,7 +108,8 @@ static __device__ __noinline__ ClipResult clipTriangleNear(const ClipInput p, ui
     return r;
   auto original = [&](int k) {
     ClipVert c;
-    c.v = finishVertex(clip[k], vz[k], hw, hh);
+    c.v     = finishVertex(clip[k], hw, hh);
+    c.viewz = vz[k];
     c.i = k;
     c.j = k;
     c.t = 0.f;
@@ -123,7 +124,8 @@ static __device__ __noinline__ ClipResult clipTriangleNear(const ClipInput p, ui
     c4[2] = 0.f;
     c4[3] = __fmaf_rn(t, __fsub_rn(clip[out][3], clip[in][3]), clip[in][3]);
     ClipVert c;
-    c.v = finishVertex(c4, __fmaf_rn(t, __fsub_rn(vz[out], vz[in]), vz[in]), hw, hh);
+    c.v     = finishVertex(c4, hw, hh);
+    c.viewz = __fmaf_rn(t, __fsub_rn(vz[out], vz[in]), vz[in]);
     c.i = in;
     c.j = out;
     c.t = t;

@@ -120,9 +120,9 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
   float vz0 = 0.f, vz1 = 0.f, vz2 = 0.f;
   if(NEED_VIEWZ)
   {
-    vz0 = clipped ? ce->v[0].viewz : p.tv[s.vidx[0]].viewz;
-    vz1 = clipped ? ce->v[m1].viewz : p.tv[s.vidx[1]].viewz;
-    vz2 = clipped ? ce->v[3 - m1].viewz : p.tv[s.vidx[2]].viewz;
+    vz0 = clipped ? ce->viewz[0] : p.tvViewz[s.vidx[0]];
+    vz1 = clipped ? ce->viewz[m1] : p.tvViewz[s.vidx[1]];
+    vz2 = clipped ? ce->viewz[3 - m1] : p.tvViewz[s.vidx[2]];
   }
   float v[7];
 #pragma unroll

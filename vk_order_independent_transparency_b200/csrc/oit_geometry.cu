@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
     for(int r = 0; r < 4; r++)
       clip[r] = __fmaf_rn(M[0 + r], px, __fmaf_rn(M[4 + r], py, __fmaf_rn(M[8 + r], pz, M[12 + r])));
     const float viewz = __fmaf_rn(V[2], px, __fmaf_rn(V[6], py, __fmaf_rn(V[10], pz, V[14])));
-    const TVert t     = finishVertex(clip, viewz, hw, hh);
-    p.tv[i] = t;
+    p.tv[i]      = finishVertex(clip, hw, hh);
+    p.tvViewz[i] = viewz;
   }
 }
 
@@ -108,12 +108,14 @@ struct TileRange
 // what the tile-range / band logic reads, BY VALUE for the out-of-line clipped path (see ClipInput)
 struct BinView
 {
-  ClipInput in;
-  int       msaa, stripTileRows, bandCount, bandIndex, tilesX;
+  ClipInput      in;
+  int            msaa, tilesX;
+  const int32_t* rowLocal;  // [tileRowsGlobal] local tile row of a global tile row this band owns, -1 for the others' rows;
+                            // nullptr when a single band owns every row (no look-ups, no integer divisions per triangle row)
 };
 __device__ __forceinline__ BinView binView(const FrameParams& p)
 {
-  return BinView{clipInput(p), p.msaa, p.stripTileRows, p.bandCount, p.bandIndex, p.tilesX};
+  return BinView{clipInput(p), p.msaa, p.tilesX, p.bandCount > 1 ? p.rowLocal : nullptr};
 }
 __device__ __forceinline__ bool tvTileRange(const BinView& v, const TVert& a, const TVert& b, const TVert& c, bool cullBack, TileRange& r)
 {
@@ -135,10 +137,12 @@ __device__ __forceinline__ bool tvTileRange(const BinView& v, const TVert& a, co
 }
 __device__ __forceinline__ uint32_t ownedTiles(const BinView& v, const TileRange& r)
 {
-  uint32_t  n  = 0;
   const int nx = r.tx1 - r.tx0 + 1;
+  if(v.rowLocal == nullptr)
+    return (uint32_t)(nx * (r.ty1 - r.ty0 + 1));
+  uint32_t n = 0;
   for(int R = r.ty0; R <= r.ty1; R++)
-    if(tileRowOwner(R, v.stripTileRows, v.bandCount) == v.bandIndex)
+    if(__ldg(v.rowLocal + R) >= 0)
       n += nx;
   return n;
 }
@@ -146,15 +150,18 @@ __device__ __forceinline__ uint32_t emitTiles(const BinView& v, const TileRange&
                                               uint32_t* __restrict__ vals)
 {
   for(int R = r.ty0; R <= r.ty1; R++)
-    if(tileRowOwner(R, v.stripTileRows, v.bandCount) == v.bandIndex)
+  {
+    const int lr = v.rowLocal ? __ldg(v.rowLocal + R) : R;
+    if(lr >= 0)
     {
-      const uint32_t rowKey = (uint32_t)tileRowToLocal(R, v.stripTileRows, v.bandCount) * v.tilesX;
+      const uint32_t rowKey = (uint32_t)lr * v.tilesX;
       for(int tx = r.tx0; tx <= r.tx1; tx++, o++)
       {
         keys[o] = rowKey + tx;
         vals[o] = val;  // emitted in primitive order; the stable sort keeps it (and the pieces of a primitive) per tile
       }
     }
+  }
   return o;
 }
 
@@ -195,6 +202,7 @@ static __device__ __noinline__ void emitClipped(const BinView v, uint32_t i0, ui
       {
         const ClipVert& cv = cr.v[s][m];
         ce.v[m]            = cv.v;
+        ce.viewz[m]        = cv.viewz;
         const float* aP    = v.in.verts + (size_t)ix[cv.i] * 10;
         const float* aQ    = v.in.verts + (size_t)ix[cv.j] * 10;
         for(int c = 0; c < 10; c++)
@@ -210,120 +218,197 @@ static __device__ __noinline__ void emitClipped(const BinView v, uint32_t i0, ui
   }
 }
 
-__global__ void __launch_bounds__(256) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
-                                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ pairInfo)
+// ------------------------------------------------------------------------------------------------------------------
+// binning: two passes over the triangles, no chain between blocks
+// ------------------------------------------------------------------------------------------------------------------
+// Pass 1 leaves ONE number per block of BIN_BLOCK consecutive triangles (its pair count); in pass 2 every block sums the
+// numbers of the blocks before it by itself (a few loads per thread), scans its own triangles and emits the (tile,
+// triangle) pairs at their final offsets IN PRIMITIVE ORDER (the stable sort keeps it per tile).  Sizing a triangle is a
+// handful of instructions on data that stays in L2, so doing it twice is cheaper than either storing per-triangle counts
+// and scanning them, or chaining the blocks of a single pass through a look-back (measured: the blocks of a wave all wait
+// for the wave's slowest loads, 45 us instead of 30).
+constexpr int BIN_TPT   = 4;              // consecutive triangles per thread
+constexpr int BIN_BLOCK = 256 * BIN_TPT;  // ... per block
+
+// the tile range + pair count of the thread's j-th triangle (n = 0: nothing to emit)
+struct BinItem
 {
-  unsigned long long nRejected = 0;
-  if(blockIdx.x == 0 && threadIdx.x == 0)
-    pairInfo[2] = 0u;  // clip entries handed out by k_bin_emit (which runs after this kernel)
-  const BinView v = binView(p);
-  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+  TileRange r;
+  uint32_t  n;
+  bool      clipped;
+};
+__device__ __forceinline__ BinItem sizeTriangle(const FrameParams& p, const BinView& v, uint32_t tri, bool cullBack, uint32_t& nRejected)
+{
+  BinItem        it;
+  const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
+  const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
+  it.n       = 0;
+  it.clipped = false;
+  if(a.x != INT32_MIN && b.x != INT32_MIN && c.x != INT32_MIN)
   {
-    const uint32_t tri = firstTri + t;
-    const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
-    const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
-    uint32_t       n = 0;
-    if(a.x != INT32_MIN && b.x != INT32_MIN && c.x != INT32_MIN)
-    {
-      TileRange r;
-      if(tvTileRange(v, a, b, c, cullBack != 0, r))
-        n = ownedTiles(v, r);
-    }
-    else
-    {
-      bool rejected;
-      n = countClipped(v, i0, i1, i2, cullBack != 0, &rejected);
-      nRejected += rejected ? 1u : 0u;
-    }
-    counts[t] = n;
+    if(tvTileRange(v, a, b, c, cullBack, it.r))
+      it.n = ownedTiles(v, it.r);
   }
-  if(nRejected)
-    atomicAdd(&p.stats[STAT_REJECTED], nRejected);
+  else
+  {
+    bool rejected;
+    it.n       = countClipped(v, i0, i1, i2, cullBack, &rejected);
+    it.clipped = true;
+    nRejected += rejected ? 1u : 0u;
+  }
+  return it;
 }
 
-// offsets[t] = exclusive prefix of the counts, offsets[triCount] = number of pairs.  Pairs beyond `capacity` are dropped
-// and the overflow flag is raised (the host then grows the buffers and renders the frame again).
-__global__ void __launch_bounds__(256) k_bin_emit(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
-                                                  const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ vals, uint32_t capacity, uint32_t* __restrict__ pairInfo)
+__global__ void __launch_bounds__(256, 4) k_bin_count(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
+                                                      uint32_t* __restrict__ blockTotals)
 {
-  if(blockIdx.x == 0 && threadIdx.x == 0)
+  __shared__ uint32_t sm[33];
+  const BinView  v  = binView(p);
+  const uint32_t t0 = blockIdx.x * BIN_BLOCK + threadIdx.x * BIN_TPT;
+  uint32_t       sum = 0, nRejected = 0;
+#pragma unroll
+  for(int j = 0; j < BIN_TPT; j++)
+    if(t0 + j < triCount)
+      sum += sizeTriangle(p, v, firstTri + t0 + j, cullBack != 0, nRejected).n;
+  uint32_t total;
+  blockExclusiveScan(sum, sm, total);
+  if(threadIdx.x == 0)
+    blockTotals[blockIdx.x] = total;
+  if(nRejected)
+    atomicAdd(&p.stats[STAT_REJECTED], (unsigned long long)nRejected);
+}
+
+// Pairs beyond `capacity` are dropped and the overflow flag is raised (the host then grows the buffers and renders the
+// frame again).  info: [0] pairs present, [1] pairs wanted, [2] clip entries handed out (zeroed before the binning)
+__global__ void __launch_bounds__(256, 4) k_bin_emit(const FrameParams p, uint32_t firstTri, uint32_t triCount, int cullBack,
+                                                     const uint32_t* __restrict__ blockTotals, uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals, uint32_t capacity, uint32_t* __restrict__ info)
+{
+  __shared__ uint32_t sm[33];
+  // pairs of all the blocks before this one
+  uint32_t before = 0;
+  for(uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x)
+    before += blockTotals[b];
+  const BinView  v  = binView(p);
+  const uint32_t t0 = blockIdx.x * BIN_BLOCK + threadIdx.x * BIN_TPT;
+  BinItem        it[BIN_TPT];
+  uint32_t       sum = 0, unused = 0;
+#pragma unroll
+  for(int j = 0; j < BIN_TPT; j++)
   {
-    const uint32_t total = offsets[triCount];
-    pairInfo[0]          = total > capacity ? 0u : total;  // pairs present (none when the frame has to be redone)
-    pairInfo[1]          = total;                 // pairs wanted
+    it[j].n = 0;
+    if(t0 + j < triCount)
+      it[j] = sizeTriangle(p, v, firstTri + t0 + j, cullBack != 0, unused);
+    sum += it[j].n;
+  }
+  uint32_t       base, blockTotal;
+  blockExclusiveScan(before, sm, base);  // (its total is the sum over the threads: the pairs before this block)
+  const uint32_t ex = blockExclusiveScan(sum, sm, blockTotal);
+  uint32_t       o  = base + ex;
+#pragma unroll
+  for(int j = 0; j < BIN_TPT; j++)
+  {
+    if(it[j].n && o + it[j].n <= capacity)
+    {
+      const uint32_t tri = firstTri + t0 + j;
+      if(!it[j].clipped)
+        emitTiles(v, it[j].r, tri, o, keys, vals);
+      else
+        emitClipped(v, p.indices[3 * (size_t)tri], p.indices[3 * (size_t)tri + 1], p.indices[3 * (size_t)tri + 2], cullBack != 0, o, keys, vals,
+                    p.clipEntries, p.clipCapacity, info + 2, p.stats + STAT_OVERFLOW);
+    }
+    o += it[j].n;
+  }
+  if(blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+  {
+    const uint32_t total = base + blockTotal;
+    info[0]              = total > capacity ? 0u : total;  // pairs present (none when the frame has to be redone)
+    info[1]              = total;                          // pairs wanted
     if(total > capacity)
       atomicAdd(&p.stats[STAT_OVERFLOW], 1ull);
   }
-  const BinView v = binView(p);
-  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
-  {
-    const uint32_t o0 = offsets[t], o1 = offsets[t + 1];
-    if(o0 == o1 || o1 > capacity)
-      continue;
-    const uint32_t tri = firstTri + t;
-    const uint32_t i0 = p.indices[3 * (size_t)tri], i1 = p.indices[3 * (size_t)tri + 1], i2 = p.indices[3 * (size_t)tri + 2];
-    const TVert    a = p.tv[i0], b = p.tv[i1], c = p.tv[i2];
-    if(a.x != INT32_MIN && b.x != INT32_MIN && c.x != INT32_MIN)
-    {
-      TileRange r;
-      if(tvTileRange(v, a, b, c, cullBack != 0, r))
-        emitTiles(v, r, tri, o0, keys, vals);
-    }
-    else
-      emitClipped(v, i0, i1, i2, cullBack != 0, o0, keys, vals, p.clipEntries, p.clipCapacity, pairInfo + 2, p.stats + STAT_OVERFLOW);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// exclusive scan of uint32 (three kernels; the middle one is a single CTA walking the block sums)
+// exclusive scan of uint32 in ONE pass: decoupled look-back (the histogram tables of the sort: a few dozen blocks)
 // ------------------------------------------------------------------------------------------------------------------
+// Blocks take a ticket with an atomic when they START, so every block with a smaller ticket is already running (or done)
+// and never waits for a later one: the look-back cannot deadlock.  A descriptor is one 64-bit word -- state in the top two
+// bits (0 = nothing yet, 1 = the block's own aggregate, 2 = inclusive prefix), value below -- written and read whole.
+// The descriptors and tickets of a frame live in BinBuffers::lb, zeroed by one memset node at the start of the binning.
+constexpr unsigned long long LB_AGGREGATE = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_VALUE = (1ull << 62) - 1ull;
+constexpr uint32_t           LB_SPIN_LIMIT = 1u << 22;  // ~0.1 s of polling: a bug must surface as an error, not as a hung GPU
+
+__device__ __forceinline__ unsigned long long lbLoad(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lbStore(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// The first WARP of the block with ticket `bid` (all 32 lanes): publishes the block's total and returns the sum of the totals
+// of all blocks before it.  The lanes inspect 32 predecessors at a time.
+__device__ __forceinline__ uint32_t lookbackExclusive(unsigned long long* desc, uint32_t bid, uint32_t total, unsigned long long* stats)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  if(lane == 0)
+    lbStore(desc + bid, (bid == 0 ? LB_INCLUSIVE : LB_AGGREGATE) | total);
+  if(bid == 0)
+    return 0u;
+  uint32_t excl = 0, spins = 0;
+  for(int window = (int)bid - 1;;)
+  {
+    const int                i     = window - (int)lane;  // lane 0 looks at the nearest predecessor
+    const unsigned long long d     = i >= 0 ? lbLoad(desc + i) : LB_INCLUSIVE;  // (before block 0: an inclusive prefix of 0)
+    const uint32_t           state = (uint32_t)(d >> 62);
+    const uint32_t           inc = __ballot_sync(0xffffffffu, state == 2u), empty = __ballot_sync(0xffffffffu, state == 0u);
+    const int                first = inc ? __ffs(inc) - 1 : 32;                       // nearest lane holding an inclusive prefix
+    const uint32_t           need  = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);  // lanes 0..first must have published
+    if(empty & need)
+    {
+      if(++spins > LB_SPIN_LIMIT)
+      {
+        if(lane == 0)
+          atomicAdd(stats + STAT_INTERNAL, 1ull);
+        break;
+      }
+      __nanosleep(20);
+      continue;
+    }
+    uint32_t v = (int)lane <= first ? (uint32_t)(d & LB_VALUE) : 0u;
+#pragma unroll
+    for(int o = 16; o; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if(first < 32)
+      break;
+    window -= 32;
+  }
+  if(lane == 0)
+    lbStore(desc + bid, LB_INCLUSIVE | (unsigned long long)(excl + total));
+  return excl;
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS   = 8;
 constexpr int SCAN_TILE    = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums)
+// out may alias in; out[n] = grand total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* desc,
+                                                                uint32_t* ticket, unsigned long long* stats)
 {
   __shared__ uint32_t sm[33];
-  const size_t        base = (size_t)blockIdx.x * SCAN_TILE;
-  uint32_t            acc  = 0;
-#pragma unroll
-  for(int k = 0; k < SCAN_ITEMS; k++)
-  {
-    const size_t i = base + (size_t)threadIdx.x * SCAN_ITEMS + k;
-    acc += i < n ? in[i] : 0u;
-  }
-  uint32_t total;
-  blockExclusiveScan(acc, sm, total);
+  __shared__ uint32_t sBid, sBase;
   if(threadIdx.x == 0)
-    sums[blockIdx.x] = total;
-}
-// in place: sums[i] <- exclusive prefix; sums[nb] <- grand total
-__global__ void __launch_bounds__(1024) k_scan_top(uint32_t* sums, size_t nb)
-{
-  __shared__ uint32_t sm[33];
-  uint32_t            carry = 0;
-  for(size_t base = 0; base < nb; base += blockDim.x)
-  {
-    const size_t   i = base + threadIdx.x;
-    const uint32_t v = i < nb ? sums[i] : 0u;
-    uint32_t       total;
-    const uint32_t ex = blockExclusiveScan(v, sm, total);
-    if(i < nb)
-      sums[i] = carry + ex;
-    carry += total;
-  }
-  if(threadIdx.x == 0)
-    sums[nb] = carry;
-}
-// out[i] = exclusive prefix of in (may alias); out[n] = grand total
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* in, size_t n, const uint32_t* __restrict__ sums,
-                                                             uint32_t* out, size_t nb)
-{
-  __shared__ uint32_t sm[33];
-  const size_t        base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-  uint32_t            v[SCAN_ITEMS];
-  uint32_t            acc = 0;
+    sBid = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t bid  = sBid;
+  const size_t   base = (size_t)bid * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t       v[SCAN_ITEMS];
+  uint32_t       acc = 0;
 #pragma unroll
   for(int k = 0; k < SCAN_ITEMS; k++)
   {
@@ -331,7 +416,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* in,
     acc += v[k];
   }
   uint32_t total;
-  uint32_t ex = blockExclusiveScan(acc, sm, total) + sums[blockIdx.x];
+  uint32_t ex = blockExclusiveScan(acc, sm, total);
+  if(threadIdx.x < 32)
+  {
+    const uint32_t excl = lookbackExclusive(desc, bid, total, stats);
+    if(threadIdx.x == 0)
+      sBase = excl;
+  }
+  __syncthreads();
+  ex += sBase;
 #pragma unroll
   for(int k = 0; k < SCAN_ITEMS; k++)
   {
@@ -339,14 +432,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* in,
       out[base + k] = ex;
     ex += v[k];
   }
-  if(blockIdx.x == 0 && threadIdx.x == 0)
-    out[n] = sums[nb];
+  if(bid == gridDim.x - 1 && threadIdx.x == 0)
+    out[n] = sBase + total;
 }
 
 static size_t scanBlocks(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 
-// exclusive scan of in[0..n) into out[0..n], out[n] = total. scratch: scanBlocks(n) + 1 words
-static int launchScan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scratch, cudaStream_t s)
+// exclusive scan of in[0..n) into out[0..n], out[n] = total.  desc: scanBlocks(n) zeroed descriptors, ticket: one zeroed word
+static int launchScan(const uint32_t* in, uint32_t* out, size_t n, unsigned long long* desc, uint32_t* ticket, unsigned long long* stats,
+                      cudaStream_t s)
 {
   const size_t nb = scanBlocks(n);
   if(nb == 0)
@@ -354,10 +448,8 @@ static int launchScan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* scr
     cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
     return 0;
   }
-  k_scan_sums<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, scratch);
-  k_scan_top<<<1, 1024, 0, s>>>(scratch, nb);
-  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, n, scratch, out, nb);
-  return 3;
+  k_scan_lookback<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(in, out, n, desc, ticket, stats);
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -377,13 +469,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __re
   const size_t base = (size_t)blockIdx.x * SORT_TILE;
   if(base < n)
   {
-#pragma unroll 4
+    // all the block's keys are requested before the first one is used (the kernel is nothing but load latency)
+    uint32_t k[SORT_ROUNDS];
+#pragma unroll
     for(int r = 0; r < SORT_ROUNDS; r++)
     {
       const size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
-      if(i < n)
-        atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+      k[r]           = i < n ? keys[i] : 0xFFFFFFFFu;
     }
+#pragma unroll
+    for(int r = 0; r < SORT_ROUNDS; r++)
+      if(base + (size_t)r * SORT_THREADS + threadIdx.x < n)
+        atomicAdd(&hist[(k[r] >> shift) & 255u], 1u);
   }
   __syncthreads();
   table[(size_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
@@ -405,13 +502,23 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* _
 #pragma unroll
   for(int w = 0; w < SORT_THREADS / 32; w++)
     cnt[w][threadIdx.x] = 0;
+  // all the block's pairs are requested up front: the rounds below are separated by barriers, and a load inside a round
+  // would expose its full latency sixteen times
+  uint32_t keyR[SORT_ROUNDS], valR[SORT_ROUNDS];
+#pragma unroll
+  for(int r = 0; r < SORT_ROUNDS; r++)
+  {
+    const size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
+    keyR[r]        = i < n ? keysIn[i] : 0u;
+    valR[r]        = i < n ? valsIn[i] : 0u;
+  }
   __syncthreads();
+#pragma unroll
   for(int r = 0; r < SORT_ROUNDS; r++)
   {
     const size_t   i      = base + (size_t)r * SORT_THREADS + threadIdx.x;
     const bool     active = i < n;
-    const uint32_t key    = active ? keysIn[i] : 0u;
-    const uint32_t val    = active ? valsIn[i] : 0u;
+    const uint32_t key = keyR[r], val = valR[r];
     const uint32_t d      = active ? ((key >> shift) & 255u) : 256u;
     const uint32_t peers  = __match_any_sync(0xffffffffu, d);
     const uint32_t rank   = __popc(peers & ((1u << lane) - 1u));
@@ -466,33 +573,47 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
 }
 
 // Launch order of the raster CTAs: heaviest tiles first, so that the light tiles fill the tail of the grid
-// (longest-processing-time-first scheduling).  A counting sort on min(list length, 1023) by ONE CTA; the order among
-// tiles of equal weight is arbitrary, which is fine: tiles are independent, the order only affects scheduling.
+// (longest-processing-time-first scheduling).  A counting sort on min(list length, 1023): a histogram pass, then every CTA
+// scans the 1024 bins for itself and places its tiles with one atomic per tile; the order among tiles of equal weight is
+// arbitrary, which is fine: tiles are independent, the order only affects scheduling.  (bins / cursors: zeroed with the
+// rest of the binning's per-frame state.)
 constexpr int ORDER_BINS = 1024;
-__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ order)
+__device__ __forceinline__ uint32_t orderBin(const uint32_t* __restrict__ tileStart, uint32_t t)
 {
-  __shared__ uint32_t bins[ORDER_BINS];
+  return (uint32_t)ORDER_BINS - 1u - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1u);  // bin 0 = heaviest
+}
+__global__ void __launch_bounds__(256) k_tile_hist(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ bins)
+{
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x)
+    atomicAdd(&bins[orderBin(tileStart, t)], 1u);
+}
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t* __restrict__ tileStart, uint32_t numTiles, const uint32_t* __restrict__ bins,
+                                                     uint32_t* __restrict__ cursors, uint32_t* __restrict__ order)
+{
+  __shared__ uint32_t binStart[ORDER_BINS];
   __shared__ uint32_t scanSm[33];
-  const int           tid = threadIdx.x;
-  bins[tid]               = 0;
+  uint32_t            total;
+  binStart[threadIdx.x] = blockExclusiveScan(bins[threadIdx.x], scanSm, total);
   __syncthreads();
-  for(uint32_t t = tid; t < numTiles; t += 1024)
-    atomicAdd(&bins[ORDER_BINS - 1 - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1)], 1u);  // bin 0 = heaviest
-  __syncthreads();
-  const uint32_t mine = bins[tid];
-  uint32_t       total;
-  const uint32_t excl = blockExclusiveScan(mine, scanSm, total);
-  bins[tid]           = excl;
-  __syncthreads();
-  for(uint32_t t = tid; t < numTiles; t += 1024)
-    order[atomicAdd(&bins[ORDER_BINS - 1 - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1)], 1u)] = t;
+  for(uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < numTiles; t += gridDim.x * blockDim.x)
+  {
+    const uint32_t b = orderBin(tileStart, t);
+    order[binStart[b] + atomicAdd(&cursors[b], 1u)] = t;
+  }
 }
 
-size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t /*numTiles*/)
+static size_t   sortBlocks(size_t pairCapacity) { return (pairCapacity + SORT_TILE - 1) / SORT_TILE; }
+static uint32_t binBlocks(size_t triCount) { return (uint32_t)((triCount + BIN_BLOCK - 1) / BIN_BLOCK); }
+
+// scratch of the sort: the [digit][block] histogram table (+ its grand total)
+size_t binScratchWords(size_t /*triCount*/, size_t pairCapacity, size_t /*numTiles*/) { return 256 * sortBlocks(pairCapacity) + 2; }
+
+// per-frame state of one binning, zeroed by one memset: [info: 4 words][tickets: 4 words][tile-order bins + cursors]
+// [look-back descriptors of the two table scans][pair count of every block of triangles]
+constexpr size_t LB_HEADER_BYTES = 32 + 2 * ORDER_BINS * sizeof(uint32_t);
+size_t binLookbackBytes(size_t triCount, size_t pairCapacity)
 {
-  const size_t sortBlocks = (pairCapacity + SORT_TILE - 1) / SORT_TILE;
-  const size_t table      = 256 * sortBlocks + 1;
-  return scanBlocks(triCount) + 2 + table + scanBlocks(table) + 2;
+  return LB_HEADER_BYTES + sizeof(unsigned long long) * (2 * scanBlocks(256 * sortBlocks(pairCapacity)) + 2) + sizeof(uint32_t) * ((size_t)binBlocks(triCount) + 2);
 }
 
 // Bins the triangles [firstTri, firstTri + triCount) of the index buffer.  On return (asynchronously) b.pairInfo[0] holds
@@ -509,23 +630,30 @@ int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint
     cudaMemsetAsync(b.pairInfo, 0, sizeof(uint32_t) * 2, s);
     return 0;
   }
-  const int blocks = (int)min((triCount + 255u) / 256u, 148u * 16u);
-  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairInfo);
-  launches += 1 + launchScan(b.counts, b.counts, triCount, b.scratch, s);
-  k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, b.counts, b.pairKey[0], b.pairVal[0],
-                                    (uint32_t)b.pairCapacity, b.pairInfo);
-  launches++;
+  // one memset: pair / clip counters, tickets, tile-order bins and the look-back descriptors of this binning
+  cudaMemsetAsync(b.lb, 0, b.lbBytes, s);
+  const uint32_t      nb       = (uint32_t)sortBlocks(b.pairCapacity);
+  const size_t        tableLen = (size_t)256 * nb;
+  uint32_t*           tickets  = b.pairInfo + 4;
+  uint32_t*           orderBins = b.pairInfo + 8;
+  unsigned long long* descScan[2];
+  descScan[0]           = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(b.lb) + LB_HEADER_BYTES);
+  descScan[1]           = descScan[0] + scanBlocks(tableLen) + 1;
+  uint32_t* blockTotals = reinterpret_cast<uint32_t*>(descScan[1] + scanBlocks(tableLen) + 1);
+  const uint32_t blocks = binBlocks(triCount);
+  k_bin_count<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, blockTotals);
+  k_bin_emit<<<blocks, 256, 0, s>>>(p, firstTri, triCount, cullBack ? 1 : 0, blockTotals, b.pairKey[0], b.pairVal[0], (uint32_t)b.pairCapacity,
+                                    b.pairInfo);
+  launches += 2;
   int bits = 1;
   while((1u << bits) < numTiles)
     bits++;
-  const uint32_t nb        = (uint32_t)((b.pairCapacity + SORT_TILE - 1) / SORT_TILE);
-  uint32_t*      table     = b.scratch + scanBlocks(triCount) + 2;
-  uint32_t*      tableScan = table + (size_t)256 * nb + 1;
-  int            cur       = 0;
-  for(int shift = 0; shift < bits; shift += 8)
+  uint32_t* table = b.scratch;
+  int       cur   = 0;
+  for(int shift = 0, pass = 0; shift < bits; shift += 8, pass++)
   {
     k_sort_hist<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairInfo, shift, table, nb);
-    launches += 1 + launchScan(table, table, (size_t)256 * nb, tableScan, s);
+    launches += 1 + launchScan(table, table, tableLen, descScan[pass & 1], tickets + (pass & 1), p.stats, s);
     k_sort_scatter<<<nb, SORT_THREADS, 0, s>>>(b.pairKey[cur], b.pairVal[cur], b.pairKey[cur ^ 1], b.pairVal[cur ^ 1], b.pairInfo, shift,
                                                table, nb);
     launches++;
@@ -535,8 +663,9 @@ int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint
   k_tile_ranges<<<rblocks, 256, 0, s>>>(b.pairKey[cur], b.pairInfo, numTiles, b.tileStart);
   launches++;
   *sortedBuf = cur;
-  k_tile_order<<<1, 1024, 0, s>>>(b.tileStart, numTiles, b.tileOrder);
-  launches++;
+  k_tile_hist<<<(int)min((numTiles + 255u) / 256u, 148u * 4u), 256, 0, s>>>(b.tileStart, numTiles, orderBins);
+  k_tile_order<<<(int)min((numTiles + 1023u) / 1024u, 148u), 1024, 0, s>>>(b.tileStart, numTiles, orderBins, orderBins + ORDER_BINS, b.tileOrder);
+  launches += 2;
   return launches;
 }
 

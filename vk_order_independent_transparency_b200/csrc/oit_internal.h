@@ -39,26 +39,28 @@ enum RasterPass
 };
 
 // post-vertex-stage vertex: object.vert.glsl:32-38 + viewport transform, snapped to 1/256 px
-struct TVert
+struct __align__(16) TVert
 {
   int32_t x, y;   // x == INT32_MIN marks a vertex outside the clip volume / guard band
   float   z;      // z_ndc = z_clip / w_clip
   float   invw;
-  float   viewz;  // (viewMatrix * pos).z  (Interpolants.depth)
 };
-static_assert(sizeof(TVert) == 20, "TVert layout");
+static_assert(sizeof(TVert) == 16, "TVert layout: one 128-bit load per vertex");
+// (viewMatrix * pos).z (Interpolants.depth, only WBOIT reads it) is a separate float per vertex: FrameParams::tvViewz
 
 // One piece of a near-clipped triangle (oit_clip.cuh), written by the binning of the frame and read by the raster kernel:
 // the piece's post-projection vertices and, per vertex, where its attributes come from.
 struct ClipEntry
 {
   TVert    v[3];      // post-projection vertices of the piece
+  float    viewz[3];  // their view-space depths
   uint32_t pad0;      // (keeps the records 8-byte aligned for the 64-bit attribute loads)
   float    attr[3][10];  // their vertex records (pos3 unused, normal3, colour4): an original vertex's, or the clip-space
                       // interpolation fma(t, attr[Q] - attr[P], attr[P]) along the cut edge -- same layout as the scene's
                       // vertex buffer, so that the shading reads either through the same code
   uint32_t pad[2];
 };
+static_assert(offsetof(ClipEntry, attr) == 64, "ClipEntry layout");
 static_assert(sizeof(ClipEntry) == 192 && offsetof(ClipEntry, attr) % 8 == 0, "ClipEntry layout");
 constexpr uint32_t PAIR_CLIPPED = 0x80000000u;  // pair value: bit 31 set = index of a ClipEntry instead of a triangle
 constexpr uint32_t PAIR_SKIP    = 0xFFFFFFFFu;  // a piece that found no room in the entry table (the frame is rendered again)
@@ -73,9 +75,10 @@ enum StatSlot
   STAT_OVERFLOW,  // the (tile, triangle) pair buffer of a draw was too small: the frame must be rendered again
   STAT_PEER_TIMEOUT,  // split frame over peer memory: a band did not arrive at the frame barrier in time
   STAT_SCRATCH,       // scene upload: index validation flag (no frame is in flight then)
+  STAT_INTERNAL,      // a look-back chain of the binning gave up (cannot happen; reported instead of hanging the GPU)
   STAT_OVERFLOW_ANY,  // split frame: SOME band raised STAT_OVERFLOW for this frame (carried by the exchange itself), so that
                       // every band takes the same decision to render the frame again
-  NUM_STAT_SLOTS = 10
+  NUM_STAT_SLOTS = 12
 };
 
 // Split frame over NVLink peer memory (oit_peer.cu): band b's resolved pixels are stored straight into the whole-frame
@@ -118,6 +121,7 @@ struct FrameParams
   // tiles
   int tilesX, tileRowsGlobal, tileRowsLocal;
   int stripTileRows, bandCount, bandIndex;
+  const int32_t* rowLocal;  // [tileRowsGlobal] local tile row of a global tile row this band owns, -1 for another band's row
   // the per-frame part of shaderio::SceneData, in device memory so that a captured frame graph can be replayed
   const DeviceUbo* ubo;
   // buffers (device)
@@ -138,6 +142,7 @@ struct FrameParams
   const float*    verts;
   const uint32_t* indices;
   TVert*          tv;
+  float*          tvViewz;  // [nVerts] behind the TVert table
   uint32_t        nVerts;
   // binning of the current draw
   const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order
@@ -184,11 +189,12 @@ void launchValidateIndices(const uint32_t* indices, uint32_t n, uint32_t nVerts,
 // d_counts/d_offsets: triCount+1 words; returns pair total through *hTotal (synchronises the stream once).
 struct BinBuffers
 {
-  uint32_t* counts;      // [triCount + 1]
+  uint32_t* lb;          // look-back state of the binning: [pairInfo 4 words][tickets 4 words][descriptors]; zeroed every frame
+  size_t    lbBytes;
   uint32_t* pairKey[2];  // [pairCapacity]
   uint32_t* pairVal[2];
   uint32_t* tileStart;   // [numLocalTiles + 1]
-  uint32_t* pairInfo;    // [0] pairs present, [1] pairs wanted (device side; read back with the statistics)
+  uint32_t* pairInfo;    // = lb: [0] pairs present, [1] pairs wanted, [2] clip entries wanted (read back with the statistics)
   uint32_t* tileOrder;   // [numLocalTiles] launch order of the tiles: heaviest lists first
   ClipEntry* clipEntries;  // [clipCapacity]; pairInfo[2] = entries wanted by the last frame
   size_t     clipCapacity;
@@ -200,6 +206,7 @@ struct BinBuffers
 int launchBin(const FrameParams& p, const BinBuffers& b, uint32_t firstTri, uint32_t triCount, bool cullBack, int* sortedBuf,
               cudaStream_t s);
 size_t binScratchWords(size_t triCount, size_t pairCapacity, size_t numTiles);
+size_t binLookbackBytes(size_t triCount, size_t pairCapacity);
 
 // band gather of the split-frame mode (oit_gather.cu); NCCL is loaded lazily with dlopen
 struct BandGatherState;
