@@ -7,5 +7,5 @@ tail -4 gpurun_out/${TAG}_tests.log
 (timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_frame.py 2>&1 | tail -8) > gpurun_out/${TAG}_memcheck.log
 tail -3 gpurun_out/${TAG}_memcheck.log
 timeout 900 python tools/bench_variants.py > gpurun_out/${TAG}_variants.log 2>&1
-OIT_B200_LAYERED_LL=1 timeout 300 python tools/bench_variants.py child >> gpurun_out/${TAG}_variants.log 2>&1
+OIT_B200_LAYERED=1 timeout 300 python tools/bench_variants.py child >> gpurun_out/${TAG}_variants.log 2>&1
 cat gpurun_out/${TAG}_variants.log

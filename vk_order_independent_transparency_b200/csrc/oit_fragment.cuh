@@ -388,40 +388,52 @@ __device__ __forceinline__ Color4 fragLock(FragCtx& c, size_t pix, size_t ai, ui
   return out;
 }
 
-// K15 oitWeighted.frag.glsl:53-79 + BlendMode::WEIGHTED_COLOR into RGBA16F / R16F (main.cpp:559-575)
-template <int S>
-__device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, int pl, uint32_t mask, const Color4& rgba, float viewz)
+// K15 oitWeighted.frag.glsl:53-79 + BlendMode::WEIGHTED_COLOR into RGBA16F / R16F (main.cpp:559-575), in two halves:
+// what the shader outputs (the weighted premultiplied colour, and 1 - alpha for the revealage target) ...
+__device__ __forceinline__ void weightedSource(const Color4& rgba, float viewz, float src[4], float& om)
 {
-  const FrameParams& p   = c.p;
-  const Color4       col = premultiply(rgba);
-  const float        depthZ = __fmul_rn(-viewz, 10.0f);
-  const float        x      = __fdiv_rn(depthZ, 200.0f);
-  const float        x2     = __fmul_rn(x, x);
-  const float        x4     = __fmul_rn(x2, x2);
-  float              distWeight = __fdiv_rn(0.03f, __fadd_rn(1e-5f, x4));
-  distWeight                    = distWeight < 1e-2f ? 1e-2f : (distWeight > 3e3f ? 3e3f : distWeight);
+  const Color4 col        = premultiply(rgba);
+  const float  depthZ     = __fmul_rn(-viewz, 10.0f);
+  const float  x          = __fdiv_rn(depthZ, 200.0f);
+  const float  x2         = __fmul_rn(x, x);
+  const float  x4         = __fmul_rn(x2, x2);
+  float        distWeight = __fdiv_rn(0.03f, __fadd_rn(1e-5f, x4));
+  distWeight              = distWeight < 1e-2f ? 1e-2f : (distWeight > 3e3f ? 3e3f : distWeight);
   const float mx     = fmaxf(fmaxf(col.r, col.g), fmaxf(col.b, col.a));
   float       aw     = fminf(1.0f, __fmaf_rn(mx, 40.0f, 0.01f));
   aw                 = __fmul_rn(aw, aw);
   const float weight = __fmul_rn(aw, distWeight);
-  const float om     = __fsub_rn(1.0f, col.a);
-  const float src[4] = {__fmul_rn(col.r, weight), __fmul_rn(col.g, weight), __fmul_rn(col.b, weight), __fmul_rn(col.a, weight)};
+  om                 = __fsub_rn(1.0f, col.a);
+  src[0]             = __fmul_rn(col.r, weight);
+  src[1]             = __fmul_rn(col.g, weight);
+  src[2]             = __fmul_rn(col.b, weight);
+  src[3]             = __fmul_rn(col.a, weight);
+}
+// ... and the ROP on one covered sample: add on RGBA16F (fp16 -> fp32, add, round to nearest even back to fp16, two channels
+// per conversion), multiply on R16F
+__device__ __forceinline__ void weightedBlendSample(uint2* acc, uint16_t* rev, const float src[4], float om)
+{
+  const uint2   a   = *acc;
+  const float2  rg  = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+  const float2  ba  = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+  const __half2 nrg = __floats2half2_rn(__fadd_rn(rg.x, src[0]), __fadd_rn(rg.y, src[1]));
+  const __half2 nba = __floats2half2_rn(__fadd_rn(ba.x, src[2]), __fadd_rn(ba.y, src[3]));
+  *acc              = make_uint2(*reinterpret_cast<const uint32_t*>(&nrg), *reinterpret_cast<const uint32_t*>(&nba));
+  *rev              = f2h(__fmul_rn(h2f(*rev), om));
+}
+template <int S>
+__device__ __forceinline__ void fragWeighted(FragCtx& c, size_t pix, int pl, uint32_t mask, const Color4& rgba, float viewz)
+{
+  const FrameParams& p = c.p;
+  float              src[4], om;
+  weightedSource(rgba, viewz, src, om);
   // the pixel's S accumulator / revealage samples: shared-memory tile (fused frame) or the global images
   uint2*    acc = c.wAccTile ? c.wAccTile + pl * S : reinterpret_cast<uint2*>(p.wacc) + pix * S;
   uint16_t* rev = c.wRevTile ? c.wRevTile + pl * S : p.wrev + pix * S;
 #pragma unroll
   for(int s = 0; s < S; s++)
     if(mask & (1u << s))
-    {
-      // ROP add on RGBA16F: fp16 -> fp32, add, round to nearest even back to fp16, two channels per conversion
-      const uint2   a  = acc[s];
-      const float2  rg = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
-      const float2  ba = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-      const __half2 nrg = __floats2half2_rn(__fadd_rn(rg.x, src[0]), __fadd_rn(rg.y, src[1]));
-      const __half2 nba = __floats2half2_rn(__fadd_rn(ba.x, src[2]), __fadd_rn(ba.y, src[3]));
-      acc[s]            = make_uint2(*reinterpret_cast<const uint32_t*>(&nrg), *reinterpret_cast<const uint32_t*>(&nba));
-      rev[s]            = f2h(__fmul_rn(h2f(rev[s]), om));
-    }
+      weightedBlendSample(acc + s, rev + s, src, om);
   c.nStored++;
 }
 
@@ -493,6 +505,101 @@ __device__ __forceinline__ void invoke(FragCtx& c, int x, int yl, uint32_t sampl
     case PASS_WEIGHTED: fragWeighted<S>(c, pixG, pl, mask, rgba, viewz); return;
   }
   ropSamples<S>(c, colorPx, mask, out);
+}
+
+// ---- the same programs with the pixel EXCLUSIVELY OWNED and its fragments arriving in primitive order -----------------------
+// (oit_raster_q.cu: one owner thread per pixel and batch walks the pixel's fragments in order.)  Mutual exclusion is
+// structural there, so the atomics of the GLSL become plain read-modify-writes on the owner's slice; what each program leaves
+// in the A-buffer and hands to the ROP is what the cascade of atomics leaves under the sequential schedule.
+
+// K6 (oitLoop.frag.glsl:57-100): the L smallest DISTINCT depths, ascending.  The atomicMin cascade = a sorted insert that
+// carries the displaced value on, stops at an empty slot or at an equal depth, and drops what falls off the end.
+__device__ __forceinline__ void ownedLoopDepth(FragCtx& c, size_t pix, uint32_t sampleID, float z)
+{
+  const FrameParams& p        = c.p;
+  const size_t       viewSize = c.viewSize;
+  uint32_t*          list     = c.abuf + viewSize * p.L * 2 * sampleID + pix;
+  uint32_t           zcur     = __float_as_uint(z);
+  if(zcur > list[(size_t)(p.L - 1) * viewSize])
+    return;
+  for(int i = 0; i < p.L; i++)
+  {
+    const uint32_t ztest = list[(size_t)i * viewSize];
+    if(ztest == zcur)
+      return;
+    if(ztest > zcur)
+    {
+      list[(size_t)i * viewSize] = zcur;
+      if(ztest == 0xFFFFFFFFu)
+        return;
+      zcur = ztest;
+    }
+  }
+}
+
+// K9 (oitLoop64.frag.glsl:65-141): the L smallest depth|colour keys, ascending; a key that does not fit -- the new one, or
+// the largest one it displaces -- is tail blended
+__device__ __forceinline__ Color4 ownedLoop64(FragCtx& c, size_t pix, uint32_t sampleID, const Color4& rgba, float z)
+{
+  const FrameParams&  p        = c.p;
+  const size_t        viewSize = c.viewSize;
+  unsigned long long* list     = reinterpret_cast<unsigned long long*>(c.abuf) + viewSize * p.L * sampleID + pix;
+  unsigned long long  zcur     = ((unsigned long long)__float_as_uint(z) << 32) | packColor(c.t, rgba);
+  if(!(zcur > list[(size_t)(p.L - 1) * viewSize]))
+    for(int i = 0; i < p.L; i++)
+    {
+      const unsigned long long ztest = list[(size_t)i * viewSize];
+      if(ztest > zcur)
+      {
+        list[(size_t)i * viewSize] = zcur;
+        if(ztest == ~0ull)
+        {
+          c.nStored++;
+          return zeroColor();
+        }
+        zcur = ztest;
+      }
+    }
+  if(p.tailBlend)
+  {
+    c.nTail++;
+    return premultiply(unpackColor(c.t, (uint32_t)(zcur & 0xFFFFFFFFull)));
+  }
+  return zeroColor();
+}
+
+// one colour-pass invocation of an owned pixel; returns the colour it hands to the ROP (premultiplied; zero = nothing)
+template <int PASS, int S>
+__device__ __forceinline__ Color4 invokeOwned(FragCtx& c, int x, int yl, uint32_t sampleID, uint32_t mask, const Color4& rgba, float z, float viewz,
+                                              int pl)
+{
+  const FrameParams& p    = c.p;
+  const size_t       pixG = (size_t)yl * p.W + x;          // pixel index in the global images
+  const size_t       pix  = c.onChip ? (size_t)pl : pixG;  // pixel index in the A-buffer slice being used
+  const size_t       ai   = (size_t)sampleID * c.viewSize + pix;
+  if(PASS == PASS_LOOP_DEPTH)
+  {
+    ownedLoopDepth(c, pix, sampleID, z);
+    return zeroColor();
+  }
+  c.nFrag++;
+  Color4 out = zeroColor();
+  switch(PASS)
+  {
+    case PASS_SIMPLE: {
+      const uint32_t old = c.aux[ai];  // imageAtomicAdd(imgAux, coord, 1u)
+      c.aux[ai]          = old + 1u;
+      out                = fragSimple(c, pix, old, sampleID, mask, rgba, z);
+      break;
+    }
+    case PASS_LINKEDLIST: out = fragLinkedList(c, ai, allocLinkedListNode(p), mask, rgba, z); break;
+    case PASS_LOOP_COLOR: out = fragLoopColor(c, pix, sampleID, rgba, z); break;
+    case PASS_LOOP64: out = ownedLoop64(c, pix, sampleID, rgba, z); break;
+    case PASS_SPINLOCK:   // the lock word is never contended: the critical section runs as under the ordered interlock
+    case PASS_INTERLOCK: out = fragLock<false>(c, pix, ai, sampleID, mask, rgba, z); break;
+    case PASS_WEIGHTED: fragWeighted<S>(c, pixG, pl, mask, rgba, viewz); break;
+  }
+  return out;
 }
 
 }  // namespace oit

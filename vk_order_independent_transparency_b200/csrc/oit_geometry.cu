@@ -229,6 +229,7 @@ static __device__ __noinline__ void emitClipped(const BinView v, uint32_t i0, ui
 // for the wave's slowest loads, 45 us instead of 30).
 constexpr int BIN_TPT   = 4;              // consecutive triangles per thread
 constexpr int BIN_BLOCK = 256 * BIN_TPT;  // ... per block
+constexpr int BIN_STAGE = 3072;           // pairs a block collects in shared memory before writing them out
 
 // the tile range + pair count of the thread's j-th triangle (n = 0: nothing to emit)
 struct BinItem
@@ -304,20 +305,37 @@ __global__ void __launch_bounds__(256, 4) k_bin_emit(const FrameParams p, uint32
   uint32_t       base, blockTotal;
   blockExclusiveScan(before, sm, base);  // (its total is the sum over the threads: the pairs before this block)
   const uint32_t ex = blockExclusiveScan(sum, sm, blockTotal);
-  uint32_t       o  = base + ex;
+  // The block's pairs are collected in shared memory and leave as two coalesced streams (a thread's own pairs are a run of
+  // one to four words: written directly, a warp's store touches up to 32 sectors); blocks with very large triangles write
+  // directly.
+  __shared__ uint32_t stageKeys[BIN_STAGE], stageVals[BIN_STAGE];
+  const bool          staged = blockTotal <= (uint32_t)BIN_STAGE && base + blockTotal <= capacity;
+  uint32_t*           dk     = staged ? stageKeys : keys;
+  uint32_t*           dv     = staged ? stageVals : vals;
+  uint32_t            o      = (staged ? 0u : base) + ex;
+  const uint32_t      limit  = staged ? (uint32_t)BIN_STAGE : capacity;
 #pragma unroll
   for(int j = 0; j < BIN_TPT; j++)
   {
-    if(it[j].n && o + it[j].n <= capacity)
+    if(it[j].n && o + it[j].n <= limit)
     {
       const uint32_t tri = firstTri + t0 + j;
       if(!it[j].clipped)
-        emitTiles(v, it[j].r, tri, o, keys, vals);
+        emitTiles(v, it[j].r, tri, o, dk, dv);
       else
-        emitClipped(v, p.indices[3 * (size_t)tri], p.indices[3 * (size_t)tri + 1], p.indices[3 * (size_t)tri + 2], cullBack != 0, o, keys, vals,
+        emitClipped(v, p.indices[3 * (size_t)tri], p.indices[3 * (size_t)tri + 1], p.indices[3 * (size_t)tri + 2], cullBack != 0, o, dk, dv,
                     p.clipEntries, p.clipCapacity, info + 2, p.stats + STAT_OVERFLOW);
     }
     o += it[j].n;
+  }
+  if(staged)
+  {
+    __syncthreads();
+    for(uint32_t i = threadIdx.x; i < blockTotal; i += blockDim.x)
+    {
+      keys[base + i] = stageKeys[i];
+      vals[base + i] = stageVals[i];
+    }
   }
   if(blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
   {

@@ -467,25 +467,26 @@ static void launchPass(const FrameParams& p, cudaStream_t s)
   }
 }
 
-// OIT_B200_LAYERED_LL=1: the linked list through the generic primitive-ordered kernel (A/B comparisons, tests)
-static bool useLayeredLinkedList()
-{
-  return getenv("OIT_B200_LAYERED_LL") != nullptr;  // (read when a frame is issued or captured, not per replay)
-}
+// OIT_B200_LAYERED=1: every pass through the layered kernel of this file (the round-1 design: tickets + one barrier per
+// layer), kept for A/B comparisons and as a second implementation the tests run against the same checker;
+// OIT_B200_LAYERED_LL=1: only the linked list.  (Read when a frame is issued or captured, not per replay.)
+static bool useLayered() { return getenv("OIT_B200_LAYERED") != nullptr; }
+static bool useLayeredLinkedList() { return useLayered() || getenv("OIT_B200_LAYERED_LL") != nullptr; }
 
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s)
 {
   if(p.tilesX * p.tileRowsLocal == 0)
     return 0;
+  // without sample shading the linked list has its own order-free kernel (oit_raster_ll.cu); every other pass shades
+  // densely and inserts in primitive order (oit_raster_q.cu)
+  if(pass == PASS_LINKEDLIST && !p.sampleShading && !useLayeredLinkedList())
+    return launchRasterLinkedList(p, s);
+  if(!useLayered() && !(pass == PASS_LINKEDLIST && useLayeredLinkedList()))
+    return launchRasterQueued(p, pass, s);
   switch(pass)
   {
     case PASS_SIMPLE: launchPass<PASS_SIMPLE>(p, s); break;
-    case PASS_LINKEDLIST:
-      // without sample shading the linked list has its own order-free kernel (oit_raster_ll.cu)
-      if(!p.sampleShading && !useLayeredLinkedList())
-        return launchRasterLinkedList(p, s);
-      launchPass<PASS_LINKEDLIST>(p, s);
-      break;
+    case PASS_LINKEDLIST: launchPass<PASS_LINKEDLIST>(p, s); break;
     case PASS_LOOP_COLOR: launchPass<PASS_LOOP_COLOR>(p, s); break;
     case PASS_LOOP64: launchPass<PASS_LOOP64>(p, s); break;
     case PASS_SPINLOCK: launchPass<PASS_SPINLOCK>(p, s); break;

@@ -257,4 +257,130 @@ __host__ __device__ constexpr int passAlgorithm(int pass)
                                : -1;
 }
 
+// ---- phases shared by the batch kernels (oit_raster_ll.cu, oit_raster_q.cu) --------------------------------------------------
+// A chunk stages CHUNK triangles (slots) whose candidates -- (triangle, pixel) pairs of the triangles' boxes inside the tile,
+// row-major per triangle, padded to ITEMS_PER_THREAD -- form one item space (itemStart[slot] = first item of the slot).
+//
+// Coverage of the thread's ITEMS_PER_THREAD consecutive candidates k .. of one triangle: recs[j] = slot | lx << 8 | ly << 12 |
+// mask << 16 (0 = not covered), and the covered pixel's bit `slot` is set in its per-batch triangle set (4 words per pixel).
+template <int S, int CHUNK>
+__device__ __forceinline__ void coverCandidates(const FrameParams& p, const TriSlot* slots, const uint32_t* itemStart, uint32_t k, uint32_t total,
+                                                int tileX0, int tileY0, int yLocal0, uint32_t* setWords, uint32_t (&recs)[ITEMS_PER_THREAD])
+{
+#pragma unroll
+  for(int j = 0; j < ITEMS_PER_THREAD; j++)
+    recs[j] = 0u;
+  if(k < total)
+  {
+    int slot = 0;
+#pragma unroll
+    for(int step = CHUNK / 2; step; step >>= 1)
+      if(itemStart[slot + step] <= k)
+        slot += step;
+    const TriSlot& s      = slots[slot];
+    const uint32_t box    = s.box;
+    const uint32_t bw     = ((box >> 8) & 15u) + 1u, nPix = bw * (((box >> 12) & 15u) + 1u);
+    const uint32_t local0 = k - itemStart[slot];
+    uint32_t       row    = (local0 * s.rcpW) >> 16, col = local0 - row * bw;
+    // all the masks first, the shared-memory atomics afterwards: nothing in between forces the slot to be read again
+    uint32_t masks[ITEMS_PER_THREAD], pls[ITEMS_PER_THREAD];
+    if(box & (1u << 20))
+    {
+      // extent <= 64 px: int32 edge functions, stepped from candidate to candidate (+1 px in x, or to the next box row)
+      int e[3], pk[3], stepX[3], stepRow[3];  // stepX: one pixel to the right; stepRow: to the first pixel of the next box row
+      {
+        const int ox = (tileX0 + (int)(box & 15u) + (int)col) << 8, oy = (tileY0 + (int)((box >> 4) & 15u) + (int)row) << 8;
+#pragma unroll
+        for(int q = 0; q < 3; q++)
+        {
+          const int a = (q + 1) % 3, b = (q + 2) % 3;
+          const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
+          pk[q]       = (int)(((uint32_t)dx & 0xFFFFu) | ((uint32_t)(-dy) << 16));
+          e[q]        = dx * (oy - s.y[a]) - dy * (ox - s.x[a]) - (int)((box >> (16 + q)) & 1u);
+          stepX[q]    = -(dy << 8);
+          stepRow[q]  = (dx << 8) + (dy << 8) * (int)(bw - 1u);
+        }
+      }
+#pragma unroll
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+      {
+        pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
+        masks[j] = 0u;
+        if(local0 + j < nPix)
+          masks[j] = sampleMaskSmall<S>(e, pk);
+        if(j + 1 < ITEMS_PER_THREAD)
+        {
+          col++;
+          const bool wrap = col == bw;
+#pragma unroll
+          for(int q = 0; q < 3; q++)
+            e[q] += wrap ? stepRow[q] : stepX[q];
+          if(wrap)
+          {
+            col = 0u;
+            row++;
+          }
+        }
+      }
+    }
+    else
+    {
+      // a triangle larger than 64 px: 64-bit edge functions, out of line (rare)
+#pragma unroll
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+      {
+        pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
+        masks[j] = 0u;
+        if(local0 + j < nPix)
+          masks[j] = coverageMaskLarge<S>(s, (tileX0 + (int)(pls[j] & 15u)) << 8, (tileY0 + (int)(pls[j] >> 4)) << 8);
+        if(++col == bw)
+        {
+          col = 0u;
+          row++;
+        }
+      }
+    }
+    if(p.depth != nullptr || !((box >> 19) & 1u))
+    {
+      // early per-sample depth test against the opaque pass (or a vertex depth close to the clear value): out of line
+#pragma unroll
+      for(int j = 0; j < ITEMS_PER_THREAD; j++)
+        if(masks[j])
+        {
+          const int    lx = (int)(pls[j] & 15u), ly = (int)(pls[j] >> 4);
+          const float* dpx = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
+          masks[j]         = depthTestMask<S>(s, (tileX0 + lx) << 8, (tileY0 + ly) << 8, dpx, masks[j]);
+        }
+    }
+#pragma unroll
+    for(int j = 0; j < ITEMS_PER_THREAD; j++)
+      if(masks[j])
+      {
+        recs[j] = (uint32_t)slot | (pls[j] << 8) | (masks[j] << 16);
+        atomicOr(&setWords[pls[j] * 4 + (slot >> 5)], 1u << (slot & 31));
+      }
+  }
+}
+
+// appends the thread's covered candidates to the batch's compact (unordered) list; *counter = length of the list
+__device__ __forceinline__ void appendCovered(const uint32_t (&recs)[ITEMS_PER_THREAD], uint32_t* counter, uint32_t* list)
+{
+  const int lane = threadIdx.x & 31;
+  uint32_t  cnt  = 0;
+#pragma unroll
+  for(int j = 0; j < ITEMS_PER_THREAD; j++)
+    cnt += recs[j] ? 1u : 0u;
+  const uint32_t incl  = warpInclusiveScan(cnt);
+  const uint32_t wtot  = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t       wbase = 0;
+  if(lane == 31 && wtot)
+    wbase = atomicAdd(counter, wtot);
+  wbase        = __shfl_sync(0xffffffffu, wbase, 31);
+  uint32_t pos = wbase + incl - cnt;
+#pragma unroll
+  for(int j = 0; j < ITEMS_PER_THREAD; j++)
+    if(recs[j])
+      list[pos++] = recs[j];
+}
+
 }  // namespace oit

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
   __shared__ uint32_t   prevHead[TILE_PIX];  // ... before the current batch
   __shared__ uint32_t   pixOff[TILE_PIX];    // first node (relative to the batch's base) of the pixel's fragments
   __shared__ uint32_t   pixPre[TILE_PIX];    // fragments in set words 0..w-1, one byte per word w
-  __shared__ uint32_t   warpTot[RASTER_THREADS / 32];
+  __shared__ __align__(16) uint32_t warpTot[RASTER_THREADS / 32];
   __shared__ uint32_t   sCount[2];
   __shared__ uint32_t   sBase;
   __shared__ uint32_t   scanSm[33];
@@ -175,118 +175,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       // ---- A: coverage of LL_IPT consecutive candidates of one triangle; compact list of the covered ones --------------------
       if(tid == 0)
         sCount[par ^ 1u] = 0u;
-      uint32_t       recs[LL_IPT];
-      const uint32_t k = k0 + tid * LL_IPT;
-#pragma unroll
-      for(int j = 0; j < LL_IPT; j++)
-        recs[j] = 0u;
-      if(k < total)
-      {
-        int slot = 0;
-#pragma unroll
-        for(int step = LL_CHUNK / 2; step; step >>= 1)
-          if(itemStart[slot + step] <= k)
-            slot += step;
-        const TriSlot& s      = slots[slot];
-        const uint32_t box    = s.box;
-        const uint32_t bw     = ((box >> 8) & 15u) + 1u, nPix = bw * (((box >> 12) & 15u) + 1u);
-        const uint32_t local0 = k - itemStart[slot];
-        uint32_t       row    = (local0 * s.rcpW) >> 16, col = local0 - row * bw;
-        // all the masks first, the shared-memory atomics afterwards: nothing in between forces the slot to be read again
-        uint32_t masks[LL_IPT], pls[LL_IPT];
-        if(box & (1u << 20))
-        {
-          // extent <= 64 px: int32 edge functions, stepped from candidate to candidate (+1 px in x, or to the next box row)
-          int e[3], pk[3], stepX[3], stepRow[3];  // stepX: one pixel to the right; stepRow: to the first pixel of the next box row
-          {
-            const int ox = (tileX0 + (int)(box & 15u) + (int)col) << 8, oy = (tileY0 + (int)((box >> 4) & 15u) + (int)row) << 8;
-#pragma unroll
-            for(int q = 0; q < 3; q++)
-            {
-              const int a = (q + 1) % 3, b = (q + 2) % 3;
-              const int dx = s.x[b] - s.x[a], dy = s.y[b] - s.y[a];
-              pk[q]       = (int)(((uint32_t)dx & 0xFFFFu) | ((uint32_t)(-dy) << 16));
-              e[q]        = dx * (oy - s.y[a]) - dy * (ox - s.x[a]) - (int)((box >> (16 + q)) & 1u);
-              stepX[q]    = -(dy << 8);
-              stepRow[q]  = (dx << 8) + (dy << 8) * (int)(bw - 1u);
-            }
-          }
-#pragma unroll
-          for(int j = 0; j < LL_IPT; j++)
-          {
-            pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
-            masks[j] = 0u;
-            if(local0 + j < nPix)
-              masks[j] = sampleMaskSmall<S>(e, pk);
-            if(j + 1 < LL_IPT)
-            {
-              col++;
-              const bool wrap = col == bw;
-#pragma unroll
-              for(int q = 0; q < 3; q++)
-                e[q] += wrap ? stepRow[q] : stepX[q];
-              if(wrap)
-              {
-                col = 0u;
-                row++;
-              }
-            }
-          }
-        }
-        else
-        {
-          // a triangle larger than 64 px: 64-bit edge functions, out of line (rare)
-#pragma unroll
-          for(int j = 0; j < LL_IPT; j++)
-          {
-            pls[j]   = ((box & 15u) + col) | ((((box >> 4) & 15u) + row) << 4);
-            masks[j] = 0u;
-            if(local0 + j < nPix)
-              masks[j] = coverageMaskLarge<S>(s, (tileX0 + (int)(pls[j] & 15u)) << 8, (tileY0 + (int)(pls[j] >> 4)) << 8);
-            if(++col == bw)
-            {
-              col = 0u;
-              row++;
-            }
-          }
-        }
-        if(p.depth != nullptr || !((box >> 19) & 1u))
-        {
-          // early per-sample depth test against the opaque pass (or a vertex depth close to the clear value): out of line
-#pragma unroll
-          for(int j = 0; j < LL_IPT; j++)
-            if(masks[j])
-            {
-              const int    lx = (int)(pls[j] & 15u), ly = (int)(pls[j] >> 4);
-              const float* dpx = p.depth ? p.depth + ((size_t)(yLocal0 + ly) * p.W + tileX0 + lx) * S : nullptr;
-              masks[j]         = depthTestMask<S>(s, (tileX0 + lx) << 8, (tileY0 + ly) << 8, dpx, masks[j]);
-            }
-        }
-#pragma unroll
-        for(int j = 0; j < LL_IPT; j++)
-          if(masks[j])
-          {
-            recs[j] = (uint32_t)slot | (pls[j] << 8) | (masks[j] << 16);
-            atomicOr(&setWords[pls[j] * 4 + (slot >> 5)], 1u << (slot & 31));
-          }
-      }
-      {
-        uint32_t cnt = 0;
-#pragma unroll
-        for(int j = 0; j < LL_IPT; j++)
-          cnt += recs[j] ? 1u : 0u;
-        const uint32_t incl  = warpInclusiveScan(cnt);
-        const uint32_t wtot  = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t       wbase = 0;
-        if(lane == 31 && wtot)
-          wbase = atomicAdd(&sCount[par], wtot);
-        wbase        = __shfl_sync(0xffffffffu, wbase, 31);
-        uint32_t pos = wbase + incl - cnt;
-#pragma unroll
-        for(int j = 0; j < LL_IPT; j++)
-          if(recs[j])
-            list[pos++] = recs[j];
-      }
+      uint32_t recs[LL_IPT];
+      coverCandidates<S, LL_CHUNK>(p, slots, itemStart, k0 + tid * LL_IPT, total, tileX0, tileY0, yLocal0, setWords, recs);
+      appendCovered(recs, &sCount[par], list);
       __syncthreads();  // (1)
 
       // ---- B: thread = pixel.  Fragment count of the pixel, its node range, the new head -------------------------------------
