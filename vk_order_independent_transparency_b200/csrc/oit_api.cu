@@ -19,24 +19,43 @@ thread_local std::string g_createError;
 
 double srgbToLinearD(double c) { return c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4); }
 
-// tables[0..255] = sRGB8 code -> linear, tables[256..511] = encode thresholds (thr[0] = -inf)
-void buildTables(float* t)
-{
-  for(int v = 0; v < 256; v++)
-    t[v] = (float)srgbToLinearD(v / 255.0);
-  t[256] = -std::numeric_limits<float>::infinity();
-  for(int k = 1; k < 256; k++)
-    t[256 + k] = (float)srgbToLinearD((k - 0.5) / 255.0);
-  for(int v = 0; v < 256; v++)
-    t[512 + v] = (float)v / 255.0f;
-}
+// The device's SrgbTables (oit_device.cuh): dec[256] sRGB8 code -> linear, thr[260] encode thresholds (thr[0] = -inf,
+// thr[256..] = +inf), a255[256] = v / 255, and the encoder's bucket table.  Returns false if a bucket holds two thresholds.
+constexpr int TAB_THR = 256, TAB_A255 = 516;
 uint32_t hostEnc8(const float* t, float c)
 {
   uint32_t k = 0;
   for(uint32_t step = 128; step; step >>= 1)
-    if(c >= t[256 + k + step])
+    if(c >= t[TAB_THR + k + step])
       k += step;
   return k;
+}
+bool buildTables(unsigned char* bytes)
+{
+  float* t = reinterpret_cast<float*>(bytes);
+  for(int v = 0; v < 256; v++)
+    t[v] = (float)srgbToLinearD(v / 255.0);
+  t[TAB_THR] = -std::numeric_limits<float>::infinity();
+  for(int k = 1; k < 256; k++)
+    t[TAB_THR + k] = (float)srgbToLinearD((k - 0.5) / 255.0);
+  for(int k = 256; k < 260; k++)
+    t[TAB_THR + k] = std::numeric_limits<float>::infinity();
+  for(int v = 0; v < 256; v++)
+    t[TAB_A255 + v] = (float)v / 255.0f;
+  unsigned char* bucket = bytes + SRGB_TABLE_FLOATS * 4;
+  memset(bucket, 0, SRGB_BUCKET_BYTES);
+  bool ok = true;
+  for(uint32_t i = 0; i < SRGB_BUCKET_COUNT; i++)
+  {
+    const uint32_t loBits = (SRGB_BUCKET_BASE + i) << 16, hiBits = i + 1 < SRGB_BUCKET_COUNT ? ((SRGB_BUCKET_BASE + i + 1) << 16) - 1u : loBits;
+    float          lo, hi;
+    memcpy(&lo, &loBits, 4);
+    memcpy(&hi, &hiBits, 4);
+    const uint32_t kLo = hostEnc8(t, lo), kHi = hostEnc8(t, hi);
+    bucket[i]          = (unsigned char)kLo;
+    ok                 = ok && kHi <= kLo + 1u;
+  }
+  return ok && bucket[0] == 0 && bucket[SRGB_BUCKET_COUNT - 1] == 255;
 }
 
 struct DevBuf
@@ -598,16 +617,21 @@ int oit_create(const OitConfig* cfg, OitCtx** out)
   if(cfg->percentTransparent < 100)
     CREATE_TRY(devAlloc(c, c->depth, P * c->msaa * 4));
   CREATE_TRY(devAlloc(c, c->fin, std::max<size_t>((size_t)cfg->width * c->localOutH, 1) * 4));
-  CREATE_TRY(devAlloc(c, c->tables, 768 * sizeof(float)));
+  CREATE_TRY(devAlloc(c, c->tables, SRGB_TABLE_BYTES));
   for(int set = 0; set < numSets(c); set++)
   {
     CREATE_TRY(devAlloc(c, c->stats[set], NUM_STAT_SLOTS * sizeof(unsigned long long)));
     CREATE_CUDA(cudaMemset(c->stats[set].p, 0, c->stats[set].bytes));
     CREATE_TRY(devAlloc(c, c->uboDev[set], sizeof(DeviceUbo)));
   }
-  float tables[768];
-  buildTables(tables);
-  CREATE_CUDA(cudaMemcpy(c->tables.p, tables, sizeof(tables), cudaMemcpyHostToDevice));
+  alignas(16) unsigned char tableBytes[SRGB_TABLE_BYTES];
+  const float*              tables = reinterpret_cast<const float*>(tableBytes);
+  if(!buildTables(tableBytes))
+  {
+    c->error = "internal error: the sRGB encoder's bucket table is not one-threshold-per-bucket";
+    return cleanupFail(OIT_ERR_CUDA);
+  }
+  CREATE_CUDA(cudaMemcpy(c->tables.p, tableBytes, SRGB_TABLE_BYTES, cudaMemcpyHostToDevice));
   // clear colour (0.2, 0.2, 0.2, 0.2) linear -> B8G8R8A8_SRGB (oitRender.cpp:90)
   const uint32_t rgb = hostEnc8(tables, 0.2f);
   fp.clearColor      = rgb | (rgb << 8) | (rgb << 16) | ((uint32_t)rintf(0.2f * 255.0f) << 24);

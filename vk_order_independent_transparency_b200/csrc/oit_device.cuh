@@ -13,34 +13,30 @@ namespace oit {
 
 struct __align__(16) SrgbTables
 {
-  float dec[256];  // sRGB8 code -> linear
-  float thr[256];  // thr[k]: smallest linear value whose code is >= k; thr[0] = -inf
-  float a255[256]; // v / 255.0f
+  float   dec[256];  // sRGB8 code -> linear
+  float   thr[260];  // thr[k]: smallest linear value whose code is >= k; thr[0] = -inf, thr[256..259] = +inf
+  float   a255[256]; // v / 255.0f
+  uint8_t bucket[SRGB_BUCKET_BYTES];
 };
+static_assert(sizeof(SrgbTables) == SRGB_TABLE_BYTES && SRGB_TABLE_BYTES % 16 == 0, "layout shared with buildTables (oit_api.cu)");
 
 // (sm must be 16-byte aligned; g is the start of a cudaMalloc allocation)
 __device__ __forceinline__ void loadTables(SrgbTables& sm, const float* __restrict__ g)
 {
-  for(int i = threadIdx.x; i < 768 / 4; i += blockDim.x)
+  for(int i = threadIdx.x; i < (int)(SRGB_TABLE_BYTES / 16); i += blockDim.x)
     reinterpret_cast<float4*>(&sm)[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
-// 8-bit sRGB code of a linear value = the largest k with c >= thr[k].  A guess from the closed form (fast, inexact
-// intrinsics) is made EXACT by walking the threshold table, so the result does not depend on the guess.
+// 8-bit sRGB code of a linear value = the largest k with c >= thr[k]: the code of the value's bucket, plus one if the value
+// has passed the one threshold that can lie inside the bucket.  Exact by construction (no transcendental guess).
 __device__ __forceinline__ uint32_t enc8(const SrgbTables& t, float c)
 {
-  const float cc = fminf(fmaxf(c, 0.f), 1.f);
-  const float s  = cc < 0.0031308f ? 12.92f * cc : 1.055f * __powf(cc, 0.41666666f) - 0.055f;
-  int         k  = min(max(__float2int_rn(s * 255.0f), 0), 255);
-  // the guess is within one code of the exact answer (the intrinsics' error is ~1e-6 of a code step); one branch-free
-  // correction against the two neighbouring thresholds makes it exact.  thr[256] reads the first entry of a255 (= 0),
-  // masked out by k < 255.
-  const float lo = t.thr[k], hi = t.thr[k + 1];
-  k += (k < 255 && c >= hi) ? 1 : 0;
-  k -= (c < lo) ? 1 : 0;
-  return (uint32_t)k;
+  const float    cc  = fminf(fmaxf(c, 0.f), 1.f);  // NaN -> 0
+  const uint32_t idx = max(__float_as_uint(cc) >> 16, SRGB_BUCKET_BASE) - SRGB_BUCKET_BASE;
+  const uint32_t k   = t.bucket[idx];
+  return k + (cc >= t.thr[k + 1] ? 1u : 0u);
 }
 __device__ __forceinline__ uint32_t unorm8(float a) { return __float2uint_rn(__fmul_rn(clamp01(a), 255.0f)); }
 

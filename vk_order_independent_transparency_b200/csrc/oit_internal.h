@@ -104,6 +104,16 @@ struct DeviceUbo
   float pad[2];
 };
 
+// Bucket table of the sRGB encoder: the linear values in [2^-13, 1] are cut into buckets by the top 16 bits of their float
+// representation (128 buckets per octave); a bucket is narrower than the distance between two encode thresholds, so it
+// holds the code of its lower end and at most one threshold (checked when the table is built, oit_api.cu: buildTables).
+constexpr uint32_t SRGB_BUCKET_BASE  = 114u << 7;   // bits(2^-13) >> 16; everything below encodes to 0 (thr[1] = 1.5e-4)
+constexpr uint32_t SRGB_BUCKET_COUNT = 1665u;       // up to and including bits(1.0f) >> 16
+constexpr uint32_t SRGB_BUCKET_BYTES = 1680u;       // padded to a multiple of 16
+constexpr uint32_t SRGB_TABLE_FLOATS = 256u + 260u + 256u;
+constexpr uint32_t SRGB_TABLE_BYTES  = SRGB_TABLE_FLOATS * 4u + SRGB_BUCKET_BYTES;
+
+
 struct FrameParams
 {
   // render target (after supersample); W x H is the full frame, localH the rows this band owns
@@ -136,7 +146,7 @@ struct FrameParams
   uint16_t*            wrev;
   uint32_t*            fin;
   const PeerTable*     peers;   // split frame over peer memory: every band's whole-frame buffer (nullptr = off)
-  const float*         tables;  // [0,256): sRGB8 -> linear, [256,512): encode thresholds, [512,768): v/255
+  const float*         tables;  // the SrgbTables image (oit_device.cuh), SRGB_TABLE_BYTES
   unsigned long long*  stats;
   // geometry
   const float*    verts;

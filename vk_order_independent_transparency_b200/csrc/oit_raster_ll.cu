@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
     sCount[tid] = 0u;
   uint32_t  nFrag = 0, nStored = 0, nTail = 0;
   uint32_t  parity = 0;
+  uint32_t  ownTotal = 0;  // fragments of the pixel this thread owns, over the whole pass
   const int lo = S == 1 ? 128 : (S == 4 ? 32 : 16);  // samples sit in [lo, 256 - lo] of the pixel
   uint4*    nodes = reinterpret_cast<uint4*>(p.abuf);
   __syncthreads();
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       const uint32_t nodeBase = sBase;
       // nodes of the batch: nodeBase + 1 + q for q in [0, n) (node 0 is the list terminator); q < room fit the pool
       const uint32_t room = nodeBase + 1u < p.capacity ? p.capacity - (nodeBase + 1u) : 0u;
+      ownTotal += c;
       if(c)
       {
         pixOff[tid]           = off;
@@ -322,12 +324,30 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
     if(!emptyTile)
     {
       FusedArrays& A = *reinterpret_cast<FusedArrays*>(scratch);
+      // The composite's cost grows with the length of the pixel's list, and neighbouring pixels differ a lot (silhouettes,
+      // background): the pixels are handed to the threads in the order of their fragment counts, longest first (a counting
+      // sort of the tile's 256 pixels), so that the lanes of a warp walk, sort and blend lists of similar length.
+      const uint32_t bin = 31u - min(ownTotal, 31u);
+      if(tid < 32)
+        scanSm[tid] = 0u;
       __threadfence_block();
       __syncthreads();
-      if(ownValid)
+      const uint32_t inBin = atomicAdd(&scanSm[bin], 1u);
+      __syncthreads();
+      if(warp == 0)
       {
+        const uint32_t v = scanSm[lane];
+        scanSm[lane]     = warpInclusiveScan(v) - v;
+      }
+      __syncthreads();
+      pixOff[scanSm[bin] + inBin] = (uint32_t)tid | (headSm[tid] ? 256u : 0u);
+      __syncthreads();
+      const uint32_t mine = pixOff[tid];
+      if(mine & 256u)
+      {
+        const uint32_t px = mine & 255u;  // a pixel with a list (pixels outside the frame have none)
         const AbufView av{p.abuf, headSm, (size_t)TILE_PIX};
-        fusedCompositePixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)tid, ownPix, tileColorSm + tid * S);
+        fusedCompositePixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)px, 0, tileColorSm + px * S);
       }
     }
     __syncthreads();
