@@ -12,6 +12,8 @@ CASES = [("headline", dict(algorithm=1, aaType=4), 3840, 2160), ("ll_noaa_4k", d
          ("simple_4k", dict(algorithm=0), 3840, 2160), ("loop32_4k", dict(algorithm=2), 3840, 2160), ("loop64_4k", dict(algorithm=3), 3840, 2160),
          ("spin_4k", dict(algorithm=4), 3840, 2160), ("interlock_4k", dict(algorithm=5), 3840, 2160), ("wboit_4k", dict(algorithm=6), 3840, 2160),
          ("interlock_msaa4_1080p", dict(algorithm=5, aaType=1), 1920, 1080)]
+if os.environ.get("OIT_CASES"):
+    CASES = [c for c in CASES if c[0] in os.environ["OIT_CASES"].split(",")]
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, ROOT)
     import vk_order_independent_transparency_b200 as oit

@@ -12,7 +12,7 @@ build_one() {
   FL="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off"
   nvcc $FL $flags -c $CS/oit_raster_ll.cu -o /tmp/variant_${name}_ll.o
   if echo "$flags" | grep -q "OIT_LL_"; then cp $CS/oit_raster.o /tmp/variant_$name.o; else nvcc $FL $flags -c $CS/oit_raster.cu -o /tmp/variant_$name.o; fi
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/variants/$name.so /tmp/variant_$name.o /tmp/variant_${name}_ll.o $CS/oit_api.o $CS/oit_geometry.o $CS/oit_composite.o $CS/oit_gather.o $CS/oit_peer.o $CS/oit_scene.o -lcudart -ldl
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/variants/$name.so /tmp/variant_$name.o /tmp/variant_${name}_ll.o $CS/oit_raster_q.o $CS/oit_api.o $CS/oit_geometry.o $CS/oit_composite.o $CS/oit_gather.o $CS/oit_peer.o $CS/oit_scene.o -lcudart -ldl
   echo built $name
 }
 export -f build_one; export ROOT CS

@@ -282,7 +282,7 @@ void selectSet(OitCtx* c, int par)
   c->par      = par;
   c->fp.stats = (unsigned long long*)c->stats[par].p;
   c->fp.tv      = (TVert*)c->tv[par].p;
-  c->fp.tvViewz = c->tv[par].p ? (float*)((TVert*)c->tv[par].p + c->nVerts) : nullptr;
+  c->fp.tvAttr  = c->tv[par].p ? (float4*)((TVert*)c->tv[par].p + c->nVerts) : nullptr;
   c->fp.ubo   = (const DeviceUbo*)c->uboDev[par].p;
 }
 int numSets(const OitCtx* c) { return c->pipelined ? 2 : 1; }
@@ -747,7 +747,7 @@ static int installScene(OitCtx* c, uint32_t nVerts, uint32_t nIndices, uint32_t 
   c->graphValid = false;
   for(int set = 0; set < numSets(c); set++)
   {
-    const int r = devAlloc(c, c->tv[set], (size_t)nVerts * (sizeof(TVert) + sizeof(float)));  // [TVert table][view-space depths]
+    const int r = devAlloc(c, c->tv[set], (size_t)nVerts * (sizeof(TVert) + ATTR_FLOATS * sizeof(float)));  // [TVert table][attribute records]
     if(r != OIT_OK)
       return r;
   }

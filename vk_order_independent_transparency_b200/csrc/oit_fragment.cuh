@@ -102,28 +102,19 @@ __device__ __forceinline__ Color4 shadeAt(const FrameParams& p, const TriSlot& s
   const bool       clipped = (s.box & SLOT_CLIPPED) != 0;
   const ClipEntry* ce      = p.clipEntries + s.vidx[0];
   const int        m1      = (s.box & SLOT_SWAPPED) ? 2 : 1;
-  const float*     a0      = clipped ? ce->attr[0] : p.verts + (size_t)s.vidx[0] * 10;
-  const float*     a1      = clipped ? ce->attr[m1] : p.verts + (size_t)s.vidx[1] * 10;
-  const float*     a2      = clipped ? ce->attr[3 - m1] : p.verts + (size_t)s.vidx[2] * 10;
-  // normal (3 floats at byte 12) + colour (4 floats at byte 24) of each vertex: one 32-bit and three 64-bit loads
-  float v0[7], v1[7], v2[7];
-  auto  fetch = [](const float* a, float* o) {
-    o[0]            = __ldg(a + 3);
-    const float2 n  = __ldg(reinterpret_cast<const float2*>(a + 4));
-    const float2 c0 = __ldg(reinterpret_cast<const float2*>(a + 6));
-    const float2 c1 = __ldg(reinterpret_cast<const float2*>(a + 8));
-    o[1] = n.x; o[2] = n.y; o[3] = c0.x; o[4] = c0.y; o[5] = c1.x; o[6] = c1.y;
+  const float4*    a0      = clipped ? reinterpret_cast<const float4*>(ce->attr[0]) : p.tvAttr + 2 * (size_t)s.vidx[0];
+  const float4*    a1      = clipped ? reinterpret_cast<const float4*>(ce->attr[m1]) : p.tvAttr + 2 * (size_t)s.vidx[1];
+  const float4*    a2      = clipped ? reinterpret_cast<const float4*>(ce->attr[3 - m1]) : p.tvAttr + 2 * (size_t)s.vidx[2];
+  // normal + colour + view depth of each vertex: two 128-bit loads (written by the vertex stage / the binning of this frame)
+  float v0[8], v1[8], v2[8];
+  auto  fetch = [](const float4* a, float* o) {
+    const float4 x = __ldg(a), y = __ldg(a + 1);
+    o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
   };
   fetch(a0, v0);
   fetch(a1, v1);
   fetch(a2, v2);
-  float vz0 = 0.f, vz1 = 0.f, vz2 = 0.f;
-  if(NEED_VIEWZ)
-  {
-    vz0 = clipped ? ce->viewz[0] : p.tvViewz[s.vidx[0]];
-    vz1 = clipped ? ce->viewz[m1] : p.tvViewz[s.vidx[1]];
-    vz2 = clipped ? ce->viewz[3 - m1] : p.tvViewz[s.vidx[2]];
-  }
+  const float vz0 = v0[7], vz1 = v1[7], vz2 = v2[7];
   float v[7];
 #pragma unroll
   for(int k = 0; k < 7; k++)

@@ -1,7 +1,9 @@
 // oit_fused.cuh -- composite + resolve of ONE tile by the CTA that has just finished the tile's colour pass.
 //
 // Same programs as oit_composite.cu (K3/K5/K8/K10/K12/K14/K16 + copyOffscreenToBackBuffer, cited there), written for
-// OIT_LAYERS <= 8 with the per-pixel fragment arrays in shared memory (element i of thread t at [i][t]: conflict free).
+// OIT_LAYERS <= 8: the depths of a pixel's fragments are sorted in REGISTERS (a compare-exchange network that replays the
+// reference's bubble sort, and a select-chain insertion for the tail), together with 4-bit slot numbers that say where the
+// fragment's colour and coverage mask sit in shared memory (row `slot` of thread t's column: conflict free).
 // Because the tile's list nodes / k-buffer slots were written by this SM moments ago they are read back from L1/L2, and
 // because the tile's colour samples live in shared memory the composite's ROP read-modify-write and the resolve never
 // touch HBM: only the resolved BGRA8 pixel is written.
@@ -16,63 +18,95 @@ constexpr int FUSED_LCAP = 8;  // the fused frame kernel is used for OIT_LAYERS 
 #define OIT_COMPACT_COMPOSITE 1
 #endif
 
+// What stays in shared memory per pixel: colour and coverage mask of its <= 8 sorted fragments, addressed through a slot
+// number.  The DEPTHS and the slot numbers live in registers, where the sorting happens.
 struct FusedArrays
 {
   uint32_t c[FUSED_LCAP][TILE_PIX];
-  uint32_t d[FUSED_LCAP][TILE_PIX];
   uint32_t m[FUSED_LCAP][TILE_PIX];
 };
 
-__device__ __forceinline__ bool fusedGE(uint32_t a, uint32_t b) { return __uint_as_float(a) >= __uint_as_float(b); }
-__device__ __forceinline__ bool fusedLT(uint32_t a, uint32_t b) { return __uint_as_float(a) < __uint_as_float(b); }
-
-// bubbleSort of oitCompositeDefines.glsl:51-89 on the first n entries of thread t's column (swap on >=)
-__device__ __forceinline__ void fusedBubbleSort(FusedArrays& A, int t, int n)
+// The sorted fragments of one composite invocation: depth d[k] and storage slot ix[k] (FusedArrays row) of the k-th entry.
+struct SortRegs
 {
-  for(int i = n - 2; i >= 0; --i)
+  float    d[FUSED_LCAP];
+  uint32_t ix[FUSED_LCAP];
+};
+
+// bubbleSort of oitCompositeDefines.glsl:51-89 on the first n entries, as the fixed compare-exchange network it is (swap on
+// >=, so equal depths end up exactly where the reference's loop leaves them): pass i = n-2 .. 0 compares (j, j+1), j <= i.
+// Entries are left-aligned; a pass the reference does not run (i > n-2) is predicated off, and passes that no lane of the
+// warp needs are skipped (the pixels of a warp have lists of similar length, see the callers).
+__device__ __forceinline__ void fusedSortNetwork(SortRegs& r, int n)
+{
+  const int nWarp = __reduce_max_sync(__activemask(), n);
+#pragma unroll
+  for(int i = FUSED_LCAP - 2; i >= 0; --i)
+  {
+    if(i > nWarp - 2)
+      continue;
+    const bool pass = i <= n - 2;
+#pragma unroll
     for(int j = 0; j <= i; ++j)
-      if(fusedGE(A.d[j][t], A.d[j + 1][t]))
-      {
-        const uint32_t c = A.c[j + 1][t], d = A.d[j + 1][t], m = A.m[j + 1][t];
-        A.c[j + 1][t] = A.c[j][t];
-        A.d[j + 1][t] = A.d[j][t];
-        A.m[j + 1][t] = A.m[j][t];
-        A.c[j][t]     = c;
-        A.d[j][t]     = d;
-        A.m[j][t]     = m;
-      }
+    {
+      const bool     sw = pass && r.d[j] >= r.d[j + 1];
+      const float    dl = sw ? r.d[j + 1] : r.d[j], dh = sw ? r.d[j] : r.d[j + 1];
+      const uint32_t il = sw ? r.ix[j + 1] : r.ix[j], ih = sw ? r.ix[j] : r.ix[j + 1];
+      r.d[j] = dl; r.d[j + 1] = dh; r.ix[j] = il; r.ix[j + 1] = ih;
+    }
+  }
 }
 
-// insertionSortTail / insertionSort (oitCompositeDefines.glsl:94-139); returns the colour that falls out
-template <bool TAIL>
-__device__ __forceinline__ uint32_t fusedInsert(FusedArrays& A, int t, int L, uint32_t c, uint32_t d, uint32_t m)
+// insertionSortTail / insertionSort (oitCompositeDefines.glsl:94-139) of one more fragment into the L sorted entries: the
+// new one goes in front of the first entry it is nearer than, the last entry falls out (its slot takes the new colour and
+// mask).  Returns the colour that falls out -- the new fragment's own if it is not nearer than the last entry.
+__device__ __forceinline__ uint32_t fusedInsertRegs(FusedArrays& A, int t, SortRegs& r, int L, uint32_t c, float d, uint32_t m)
 {
-  uint32_t outColor = c;
-  if(!TAIL || fusedLT(d, A.d[L - 1][t]))
-  {
-    for(int i = 0; i < L; ++i)
-      if(fusedLT(d, A.d[i][t]))
-      {
-        outColor = A.c[L - 1][t];
-        for(int j = L - 1; j > i; j--)
-        {
-          A.c[j][t] = A.c[j - 1][t];
-          A.d[j][t] = A.d[j - 1][t];
-          A.m[j][t] = A.m[j - 1][t];
-        }
-        A.c[i][t] = c;
-        A.d[i][t] = d;
-        A.m[i][t] = m;
-        break;
-      }
-  }
+  // entry L-1 (a register picked by a run-time index: a select chain; L == 8 in the default configuration)
+  float    dLast = r.d[FUSED_LCAP - 1];
+  uint32_t iLast = r.ix[FUSED_LCAP - 1];
+#pragma unroll
+  for(int j = 0; j < FUSED_LCAP - 1; j++)
+    if(j == L - 1)
+    {
+      dLast = r.d[j];
+      iLast = r.ix[j];
+    }
+  if(!(d < dLast))
+    return c;
+  const uint32_t outColor = A.c[iLast][t];
+  A.c[iLast][t]           = c;
+  A.m[iLast][t]           = m;
+  bool lt[FUSED_LCAP];
+#pragma unroll
+  for(int j = 0; j < FUSED_LCAP; j++)
+    lt[j] = d < r.d[j];
+#pragma unroll
+  for(int j = FUSED_LCAP - 1; j >= 1; j--)
+    if(j < L)
+    {
+      r.d[j]  = lt[j - 1] ? r.d[j - 1] : (lt[j] ? d : r.d[j]);
+      r.ix[j] = lt[j - 1] ? r.ix[j - 1] : (lt[j] ? iLast : r.ix[j]);
+    }
+  r.d[0]  = lt[0] ? d : r.d[0];
+  r.ix[0] = lt[0] ? iLast : r.ix[0];
   return outColor;
+}
+
+// slot numbers of the sorted entries, 4 bits each (the blend loop is not unrolled over the fragments)
+__device__ __forceinline__ uint32_t fusedPackSlots(const SortRegs& r)
+{
+  uint32_t packed = 0u;
+#pragma unroll
+  for(int k = 0; k < FUSED_LCAP; k++)
+    packed |= r.ix[k] << (4 * k);
+  return packed;
 }
 
 // blend of the sorted fragments (oitSimple.frag.glsl:138-167).  Coverage mode keeps one accumulator per sample and walks
 // the fragments once: every sample still sees its fragments front to back, so the arithmetic is the reference's.
 template <int S>
-__device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedArrays& A, int t, int n, bool coverage)
+__device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedArrays& A, int t, int n, uint32_t slots, bool coverage)
 {
   if(coverage && S > 1)
   {
@@ -85,8 +119,9 @@ __device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedAr
 #endif
     for(int i = 0; i < n; i++)
     {
-      const Color4   pm = premultiply(unpackColor(tb, A.c[i][t]));
-      const uint32_t m  = A.m[i][t];
+      const uint32_t slot = (slots >> (4 * i)) & 15u;
+      const Color4   pm   = premultiply(unpackColor(tb, A.c[slot][t]));
+      const uint32_t m    = A.m[slot][t];
 #pragma unroll
       for(int s = 0; s < S; s++)
         if(m & (1u << s))
@@ -106,7 +141,7 @@ __device__ __forceinline__ Color4 fusedBlend(const SrgbTables& tb, const FusedAr
   }
   Color4 sum = zeroColor();
   for(int i = 0; i < n; i++)
-    doBlendPacked(tb, sum, A.c[i][t]);
+    doBlendPacked(tb, sum, A.c[(slots >> (4 * i)) & 15u][t]);
   return sum;
 }
 
@@ -135,45 +170,71 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
     case OIT_INTERLOCK: {
       const size_t listPos = P * L * sampleID + pix;
       const int    n       = (int)min((uint32_t)L, av.aux[ai]);
-      for(int i = 0; i < n; i++)
+      SortRegs     r;
+#pragma unroll
+      for(int i = 0; i < FUSED_LCAP; i++)
       {
-        if(p.coverage)
+        r.d[i]  = 0.f;
+        r.ix[i] = (uint32_t)i;
+        if(i < n)
         {
-          const uint4 e = reinterpret_cast<const uint4*>(av.abuf)[listPos + (size_t)i * P];
-          A.c[i][t] = e.x; A.d[i][t] = e.y; A.m[i][t] = e.z;
-        }
-        else
-        {
-          const uint2 e = reinterpret_cast<const uint2*>(av.abuf)[listPos + (size_t)i * P];
-          A.c[i][t] = e.x; A.d[i][t] = e.y; A.m[i][t] = 0u;
+          if(p.coverage)
+          {
+            const uint4 e = reinterpret_cast<const uint4*>(av.abuf)[listPos + (size_t)i * P];
+            A.c[i][t] = e.x; r.d[i] = __uint_as_float(e.y); A.m[i][t] = e.z;
+          }
+          else
+          {
+            const uint2 e = reinterpret_cast<const uint2*>(av.abuf)[listPos + (size_t)i * P];
+            A.c[i][t] = e.x; r.d[i] = __uint_as_float(e.y); A.m[i][t] = 0u;
+          }
         }
       }
-      fusedBubbleSort(A, t, n);
-      return fusedBlend<S>(tb, A, t, n, p.coverage != 0);
+      fusedSortNetwork(r, n);
+      return fusedBlend<S>(tb, A, t, n, fusedPackSlots(r), p.coverage != 0);
     }
     case OIT_LINKEDLIST: {
       const uint4* nodes  = reinterpret_cast<const uint4*>(av.abuf);
       uint32_t     offset = av.aux[ai];
       int          n      = 0;
-      while(offset != 0u && n < L)
+      SortRegs     r;
+#ifdef OIT_EXPERIMENT_NO_CHASE
+      uint32_t remaining = (uint32_t)av.viewSize;  // timing experiment: the list is walked as if its nodes were contiguous
+      if(offset < remaining)
+        remaining = offset;
+#endif
+#pragma unroll
+      for(int i = 0; i < FUSED_LCAP; i++)
       {
-        const uint4 e = nodes[offset];
-        A.c[n][t] = e.x; A.d[n][t] = e.y; A.m[n][t] = e.z;
-        n++;
-        offset = e.w;
+        r.d[i]  = 0.f;
+        r.ix[i] = (uint32_t)i;
+        if(offset != 0u && i < L)
+        {
+          const uint4 e = nodes[offset];
+          A.c[i][t] = e.x; r.d[i] = __uint_as_float(e.y); A.m[i][t] = e.z;
+          n      = i + 1;
+#ifdef OIT_EXPERIMENT_NO_CHASE
+          offset = --remaining ? offset - 1u : 0u;
+#else
+          offset = e.w;
+#endif
+        }
       }
-      fusedBubbleSort(A, t, n);
+      fusedSortNetwork(r, n);
       Color4 tailColor = zeroColor();
       while(offset != 0u)
       {
-        const uint4 e = nodes[offset];
+        const uint4    e   = nodes[offset];
+        const uint32_t out = fusedInsertRegs(A, t, r, L, e.x, __uint_as_float(e.y), e.z);
         if(p.tailBlend)
-          doBlendPacked(tb, tailColor, fusedInsert<true>(A, t, L, e.x, e.y, e.z));
-        else
-          fusedInsert<false>(A, t, L, e.x, e.y, e.z);
+          doBlendPacked(tb, tailColor, out);
+#ifdef OIT_EXPERIMENT_NO_CHASE
+        offset = --remaining ? offset - 1u : 0u;
+#else
         offset = e.w;
+#endif
       }
-      Color4 out = fusedBlend<S>(tb, A, t, n, p.coverage != 0);
+      Color4 out = fusedBlend<S>(tb, A, t, n, fusedPackSlots(r), p.coverage != 0);
       doBlend(out, tailColor);
       return out;
     }
@@ -339,6 +400,74 @@ __device__ __forceinline__ void fusedResolveTile(const FrameParams& p, const Srg
     }
     fusedStorePixel(p, gx, gy, outW, ss, result);
   }
+}
+
+// Composite + ROP + resolve of ONE pixel whose samples nobody else touches any more (coverage shading or no AA, no
+// super-sampling: the output pixel is the pixel): the S destination samples are read once, blended and box-filtered in
+// registers, and only the resolved pixel is stored -- no barrier between the composite and the resolve of a tile.
+// `covered`: the pixel has fragments to composite (otherwise only the resolve of what the opaque pass / clear left).
+template <int S, int ALG>
+__device__ __forceinline__ void fusedFinishPixel(const FrameParams& p, const SrgbTables& tb, FusedArrays& A, int t, const AbufView& av, size_t pixA,
+                                                 const uint32_t* px, bool covered, int gx, int gyLocal)
+{
+  uint32_t v[S];
+  if(S % 4 == 0)
+  {
+#pragma unroll
+    for(int q = 0; q < S / 4; q++)
+    {
+      const uint4 w = reinterpret_cast<const uint4*>(px)[q];
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for(int s = 0; s < S; s++)
+      v[s] = px[s];
+  }
+  if(covered)
+  {
+    const Color4 out = fusedCompositeInvocation<S, ALG>(p, tb, A, t, av, pixA, 0);
+    if(!isZero(out))
+    {
+      // the same source colour goes to every sample: samples that hold the same destination word share the blend
+      uint32_t prevDst = v[0], prevRes = ropPremult(tb, prevDst, out);
+      v[0]             = prevRes;
+#pragma unroll
+      for(int s = 1; s < S; s++)
+      {
+        if(v[s] != prevDst)
+        {
+          prevDst = v[s];
+          prevRes = ropPremult(tb, prevDst, out);
+        }
+        v[s] = prevRes;
+      }
+    }
+  }
+  uint32_t result  = v[0];
+  bool     uniform = true;
+#pragma unroll
+  for(int s = 1; s < S; s++)
+    uniform = uniform && v[s] == result;
+  if(!uniform)
+  {
+    // (the box filter of identical codes is that code, see fusedResolveTile)
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for(int s = 0; s < S; s++)
+    {
+      const Color4 d = decodeDst(tb, v[s]);
+      sum[0]         = __fadd_rn(sum[0], d.r);
+      sum[1]         = __fadd_rn(sum[1], d.g);
+      sum[2]         = __fadd_rn(sum[2], d.b);
+      sum[3]         = __fadd_rn(sum[3], d.a);
+    }
+    const float inv = 1.0f / (float)S;
+    result = encodeDst(tb, Color4{__fmul_rn(sum[0], inv), __fmul_rn(sum[1], inv), __fmul_rn(sum[2], inv), __fmul_rn(sum[3], inv)});
+  }
+  fusedStorePixel(p, gx, gyLocal, p.W, 1, result);
 }
 
 // a tile nothing was drawn into (and no opaque pass ran): every sample holds the clear colour, which resolves to itself

@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(256) k_transform_vertices(const FrameParams p)
       clip[r] = __fmaf_rn(M[0 + r], px, __fmaf_rn(M[4 + r], py, __fmaf_rn(M[8 + r], pz, M[12 + r])));
     const float viewz = __fmaf_rn(V[2], px, __fmaf_rn(V[6], py, __fmaf_rn(V[10], pz, V[14])));
     p.tv[i]      = finishVertex(clip, hw, hh);
-    p.tvViewz[i] = viewz;
+    // the interpolants of the shading, repacked (oit_internal.h: ATTR_FLOATS)
+    p.tvAttr[2 * (size_t)i]     = make_float4(v[3], v[4], v[5], v[6]);
+    p.tvAttr[2 * (size_t)i + 1] = make_float4(v[7], v[8], v[9], viewz);
   }
 }
 
@@ -202,15 +204,13 @@ static __device__ __noinline__ void emitClipped(const BinView v, uint32_t i0, ui
       {
         const ClipVert& cv = cr.v[s][m];
         ce.v[m]            = cv.v;
-        ce.viewz[m]        = cv.viewz;
-        const float* aP    = v.in.verts + (size_t)ix[cv.i] * 10;
-        const float* aQ    = v.in.verts + (size_t)ix[cv.j] * 10;
-        for(int c = 0; c < 10; c++)
+        const float* aP    = v.in.verts + (size_t)ix[cv.i] * 10 + 3;
+        const float* aQ    = v.in.verts + (size_t)ix[cv.j] * 10 + 3;
+        for(int c = 0; c < 7; c++)
           ce.attr[m][c] = cv.i == cv.j ? aP[c] : __fmaf_rn(cv.t, __fsub_rn(aQ[c], aP[c]), aP[c]);
+        ce.attr[m][7] = cv.viewz;
       }
-      ce.pad0   = 0u;
-      ce.pad[0] = ce.pad[1] = 0u;
-      val                   = PAIR_CLIPPED | e;
+      val = PAIR_CLIPPED | e;
     }
     else
       atomicAdd(overflow, 1ull);  // the host grows the table and renders the frame again

@@ -46,22 +46,22 @@ struct __align__(16) TVert
   float   invw;
 };
 static_assert(sizeof(TVert) == 16, "TVert layout: one 128-bit load per vertex");
-// (viewMatrix * pos).z (Interpolants.depth, only WBOIT reads it) is a separate float per vertex: FrameParams::tvViewz
+// What the shading interpolates (shaderCommon.glsl:25-31), repacked by the vertex stage into two 128-bit words per vertex
+// behind the TVert table (FrameParams::tvAttr): [2i] = normal.xyz, colour.r; [2i+1] = colour.gba, (viewMatrix * pos).z
+// (Interpolants.depth, only WBOIT reads it).  One 32-byte sector per vertex instead of 28 bytes that straddle two sectors of
+// the 40-byte vertex record, and 2 loads instead of 4.
+constexpr int ATTR_FLOATS = 8;
 
 // One piece of a near-clipped triangle (oit_clip.cuh), written by the binning of the frame and read by the raster kernel:
 // the piece's post-projection vertices and, per vertex, where its attributes come from.
 struct ClipEntry
 {
-  TVert    v[3];      // post-projection vertices of the piece
-  float    viewz[3];  // their view-space depths
-  uint32_t pad0;      // (keeps the records 8-byte aligned for the 64-bit attribute loads)
-  float    attr[3][10];  // their vertex records (pos3 unused, normal3, colour4): an original vertex's, or the clip-space
-                      // interpolation fma(t, attr[Q] - attr[P], attr[P]) along the cut edge -- same layout as the scene's
-                      // vertex buffer, so that the shading reads either through the same code
-  uint32_t pad[2];
+  TVert v[3];                  // post-projection vertices of the piece
+  float attr[3][ATTR_FLOATS];  // their attribute records in the layout of FrameParams::tvAttr (normal3, colour4, view depth):
+                               // an original vertex's, or the clip-space interpolation fma(t, attr[Q] - attr[P], attr[P])
+                               // along the cut edge -- so that the shading reads either through the same code
 };
-static_assert(offsetof(ClipEntry, attr) == 64, "ClipEntry layout");
-static_assert(sizeof(ClipEntry) == 192 && offsetof(ClipEntry, attr) % 8 == 0, "ClipEntry layout");
+static_assert(offsetof(ClipEntry, attr) == 48 && sizeof(ClipEntry) == 144, "ClipEntry layout: 128-bit attribute loads");
 constexpr uint32_t PAIR_CLIPPED = 0x80000000u;  // pair value: bit 31 set = index of a ClipEntry instead of a triangle
 constexpr uint32_t PAIR_SKIP    = 0xFFFFFFFFu;  // a piece that found no room in the entry table (the frame is rendered again)
 
@@ -152,7 +152,7 @@ struct FrameParams
   const float*    verts;
   const uint32_t* indices;
   TVert*          tv;
-  float*          tvViewz;  // [nVerts] behind the TVert table
+  float4*         tvAttr;   // [2 * nVerts] behind the TVert table: the vertices' attribute records (see ATTR_FLOATS)
   uint32_t        nVerts;
   // binning of the current draw
   const uint32_t* pairTri;    // triangle index (first index / 3) per (tile, triangle) pair, tile-major, in order

@@ -7,16 +7,20 @@
 //   A  coverage   each thread tests ITEMS_PER_THREAD (triangle, pixel) candidates (oit_raster_common.cuh).  A covered
 //                 fragment sets bit `triangle slot` in its pixel's 128-bit set (one chunk = 128 staged triangles, so the
 //                 bit index IS the primitive order) and is appended to an unordered compact list.
-//   B  allocate   thread = pixel: popcount of the set = fragments of the pixel in this batch; one CTA scan gives every pixel
-//                 a contiguous range of the batch's nodes, ONE atomicAdd per batch on the global counter (the reference
-//                 issues one per fragment, oitLinkedList.frag.glsl:55) reserves them, and the pixel's head moves to the last.
+//   B  allocate   thread = pixel: popcount of the set = fragments of the pixel in this batch; a warp scan gives every pixel a
+//                 contiguous range of the nodes its warp reserves with ONE atomicAdd on the global counter (the reference
+//                 issues one per fragment, oitLinkedList.frag.glsl:55), and the pixel's head moves to the last of them.
 //   C  shade      dense over the compact list, any order: rank of the fragment among its pixel's = popcount of the lower
-//                 bits; node = base + pixel offset + rank; next = node - 1 (rank > 0) or the pixel's previous head.  Shade,
+//                 bits; node = pixel's first node + rank; next = node - 1 (rank > 0) or the pixel's previous head.  Shade,
 //                 pack, ONE 128-bit store.  No tickets, no layers, no per-fragment atomics, no barrier per layer.
 //
-// Three CTA barriers per batch of up to 1024 candidates.  The list heads of the tile live in shared memory for the whole
-// pass (written to imgAux once at the end); the lists are identical to the ones the sequential schedule builds (same
-// nodes per pixel in the same link order; node NUMBERS differ, like between any two runs of the reference).
+// Two CTA barriers per batch of up to 1024 candidates (after A, after B; sets and lists are double-buffered so that C of one
+// batch overlaps A of the next).  The list heads of the tile live in shared memory for the whole pass (written to imgAux
+// once at the end); the lists are identical to the ones the sequential schedule builds (same nodes per pixel in the same
+// link order; node NUMBERS differ, like between any two runs of the reference).
+//
+// Fused frame: the composite hands the tile's pixels to the threads in the order of their list lengths (counting sort), so
+// that the lanes of a warp walk, sort and blend lists of similar length.
 //
 // Pool overflow (node index >= capacity, oitLinkedList.frag.glsl:82): the overflowing fragments are tail-blended by the
 // ROP in primitive order.  The batch then takes a slower path: the fragments are permuted into pixel-major order, shaded
@@ -30,6 +34,9 @@ constexpr int LL_IPT       = ITEMS_PER_THREAD;
 constexpr int LL_BATCH     = RASTER_THREADS * LL_IPT;
 #ifndef OIT_LL_MIN_BLOCKS
 #define OIT_LL_MIN_BLOCKS 5
+#endif
+#ifndef OIT_LL_KNOCKOUT
+#define OIT_LL_KNOCKOUT 0  // timing experiments only (tools/build_variants.sh): 1 = no composite, 2 = no shading, 4 = no node store
 #endif
 
 template <int S>
@@ -50,9 +57,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
   __shared__ uint32_t   prevHead[TILE_PIX];  // ... before the current batch
   __shared__ uint32_t   pixOff[TILE_PIX];    // first node (relative to the batch's base) of the pixel's fragments
   __shared__ uint32_t   pixPre[TILE_PIX];    // fragments in set words 0..w-1, one byte per word w
-  __shared__ __align__(16) uint32_t warpTot[RASTER_THREADS / 32];
   __shared__ uint32_t   sCount[2];
-  __shared__ uint32_t   sBase;
+  __shared__ uint16_t   pixRel[TILE_PIX];    // overflow path: the pixel's first position in the batch's pixel-major order
   __shared__ uint32_t   scanSm[33];
   __shared__ uint8_t    tailMask[RASTER_THREADS];
   extern __shared__ __align__(16) unsigned char dynSmem[];  // fused frame: the tile's colour samples
@@ -123,6 +129,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
 
   // shading of one fragment record at the pixel centre (coverage shading / no AA: SURVEY 8a row R) -> packed colour, depth
   auto shadeRecord = [&](uint32_t rec, Color4& rgba, float& z) {
+    if(OIT_LL_KNOCKOUT & 2)
+    {
+      rgba = Color4{0.5f, 0.25f, 0.125f, __uint_as_float(rec)};
+      z    = 0.5f;
+      return;
+    }
     const TriSlot& s     = slots[rec & (LL_CHUNK - 1)];
     const bool     small = (s.box >> 20) & 1u;
     const int      lx = (rec >> 8) & 15, ly = (rec >> 12) & 15;
@@ -181,62 +193,54 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       appendCovered(recs, &sCount[par], list);
       __syncthreads();  // (1)
 
-      // ---- B: thread = pixel.  Fragment count of the pixel, its node range, the new head -------------------------------------
+      // ---- B: thread = pixel.  Fragment count of the pixel, its node range, the new head ---------------------------------------
+      // Every warp reserves the nodes of its 32 pixels with ONE atomicAdd on the global counter (the reference issues one
+      // per fragment, oitLinkedList.frag.glsl:55): a pixel's nodes are contiguous, the order of the ranges is free.
       const uint32_t n = sCount[par];
-      if(tid == 0)
-        sBase = n ? atomicAdd(p.counter, n) : 0u;  // imageAtomicAdd(imgCounter, 1) of every fragment of the batch, at once
-      setOther[tid]     = make_uint4(0u, 0u, 0u, 0u);  // the next batch's sets (their last readers are past barrier 1)
+      setOther[tid]    = make_uint4(0u, 0u, 0u, 0u);  // the next batch's sets (their last readers are past barrier 1)
       const uint4    m  = pixSet[par * TILE_PIX + tid];
       const uint32_t c0 = __popc(m.x), c1 = __popc(m.y), c2 = __popc(m.z), c3 = __popc(m.w);
       const uint32_t c  = c0 + c1 + c2 + c3;
-      uint32_t       off;
-      {
-        const uint32_t incl = warpInclusiveScan(c);
-        if(lane == 31)
-          warpTot[warp] = incl;
-        __syncthreads();  // (2)
-        uint32_t wb = 0;
-#pragma unroll
-        for(int v = 0; v < RASTER_THREADS / 32 - 1; v++)
-          wb += v < warp ? warpTot[v] : 0u;
-        off = wb + incl - c;
-      }
-      const uint32_t nodeBase = sBase;
-      // nodes of the batch: nodeBase + 1 + q for q in [0, n) (node 0 is the list terminator); q < room fit the pool
-      const uint32_t room = nodeBase + 1u < p.capacity ? p.capacity - (nodeBase + 1u) : 0u;
+      const uint32_t incl = warpInclusiveScan(c);
+      uint32_t       wbase = 0;
+      if(lane == 31 && incl)
+        wbase = atomicAdd(p.counter, incl);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      // the pixel's fragment of rank r gets node off + 1 + r (node 0 is the list terminator); nodes < capacity fit the pool
+      const uint32_t off    = wbase + incl - c;
+      const uint32_t room   = off + 1u < p.capacity ? p.capacity - (off + 1u) : 0u;
+      const uint32_t stored = min(c, room);
       ownTotal += c;
       if(c)
       {
-        pixOff[tid]           = off;
-        pixPre[tid]           = (c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24);
-        prevHead[tid]         = headSm[tid];
-        const uint32_t stored = off < room ? min(c, room - off) : 0u;
+        pixOff[tid]   = off;
+        pixPre[tid]   = (c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24);
+        prevHead[tid] = headSm[tid];
         if(stored)
-          headSm[tid] = nodeBase + off + stored;  // the pixel's last stored fragment
+          headSm[tid] = off + stored;  // the pixel's last stored fragment
       }
-      __syncthreads();  // (3)
+      const bool overflow = __syncthreads_or(stored < c) != 0;  // (2)
 
       // rank of a fragment among its pixel's fragments of this batch = position of its node inside the pixel's range
-      auto queuePos = [&](uint32_t rec, uint32_t& rank) {
+      auto fragRank = [&](uint32_t rec) {
         const uint32_t slot = rec & (LL_CHUNK - 1), pl = (rec >> 8) & 255u, w = slot >> 5;
-        rank                = __popc(setWords[pl * 4 + w] & ((1u << (slot & 31u)) - 1u)) + ((pixPre[pl] >> (8u * w)) & 255u);
-        return pixOff[pl] + rank;
+        return __popc(setWords[pl * 4 + w] & ((1u << (slot & 31u)) - 1u)) + ((pixPre[pl] >> (8u * w)) & 255u);
       };
 
-      if(n <= room)
+      if(!overflow)
       {
         // ---- C: shade + store, dense and in any order ------------------------------------------------------------------------
         for(uint32_t i = tid; i < n; i += RASTER_THREADS)
         {
-          const uint32_t rec = list[i];
-          uint32_t       rank;
-          const uint32_t q    = queuePos(rec, rank);
-          const uint32_t node = nodeBase + 1u + q;
-          const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
+          const uint32_t rec  = list[i];
+          const uint32_t rank = fragRank(rec), pl = (rec >> 8) & 255u;
+          const uint32_t node = pixOff[pl] + 1u + rank;
+          const uint32_t next = rank ? node - 1u : prevHead[pl];
           Color4         rgba;
           float          z;
           shadeRecord(rec, rgba, z);
-          nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
+          if(!(OIT_LL_KNOCKOUT & 4) || rgba.r == 77.f)
+            nodes[node] = make_uint4(packColor(tabs, rgba), __float_as_uint(z), S > 1 ? (rec >> 16) & 255u : 0u, next);
         }
         if(tid == 0)
         {
@@ -247,21 +251,25 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       else
       {
         // ---- the pool runs out inside (or before) this batch --------------------------------------------------------------
-        // fragments that still fit are stored as above; all are copied to their pixel-major position (into the other
-        // batch's list buffer: idle until the next batch's phase A)
+        // fragments that still fit are stored as above; all are copied to their pixel-major position of the batch (into the
+        // other batch's list buffer: idle until the next batch's phase A), which needs the CTA-wide scan of the counts
         uint32_t* sorted = lists + (par ^ 1u) * LL_BATCH;
+        uint32_t  total;
+        const uint32_t rel = blockExclusiveScan(c, scanSm, total);
+        pixRel[tid]        = (uint16_t)rel;
+        __syncthreads();
 #pragma unroll 1
         for(uint32_t i = tid; i < n; i += RASTER_THREADS)
         {
-          const uint32_t rec = list[i];
-          uint32_t       rank;
-          const uint32_t q = queuePos(rec, rank);
-          sorted[q]        = rec;
+          const uint32_t rec  = list[i];
+          const uint32_t rank = fragRank(rec), pl = (rec >> 8) & 255u;
+          const uint32_t node = pixOff[pl] + 1u + rank;
+          const bool     fits = node < p.capacity;
+          sorted[pixRel[pl] + rank] = fits ? 0u : rec;  // only the overflowing ones are looked at again
           nFrag++;
-          if(q < room)
+          if(fits)
           {
-            const uint32_t node = nodeBase + 1u + q;
-            const uint32_t next = rank ? node - 1u : prevHead[(rec >> 8) & 255u];
+            const uint32_t next = rank ? node - 1u : prevHead[pl];
             Color4         rgba;
             float          z;
             shadeRecord(rec, rgba, z);
@@ -278,23 +286,23 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
           // round, into a queue that borrows the next batch's (idle, zeroed) sets; blended by the pixel's owner in order
           float4*   queue = reinterpret_cast<float4*>(setOther);
           uint32_t* px    = tileColor ? tileColor + tid * S : p.color + ownPix * S;
-          for(uint32_t r0 = min(room, n); r0 < n; r0 += RASTER_THREADS)
+          for(uint32_t r0 = 0; r0 < n; r0 += RASTER_THREADS)
           {
-            const uint32_t i = r0 + tid;
-            if(i < n)
+            const uint32_t i   = r0 + tid;
+            const uint32_t rec = i < n ? sorted[i] : 0u;
+            if(rec)
             {
-              const uint32_t rec = sorted[i];
-              Color4         rgba;
-              float          z;
+              Color4 rgba;
+              float  z;
               shadeRecord(rec, rgba, z);
               const Color4 pm = premultiply(rgba);
               queue[tid]      = make_float4(pm.r, pm.g, pm.b, pm.a);
               tailMask[tid]   = (uint8_t)((rec >> 16) & 255u);
             }
             __syncthreads();
-            if(c)
+            if(stored < c)
             {
-              const uint32_t qa = max(off, r0), qb = min(off + c, min(r0 + RASTER_THREADS, n));
+              const uint32_t qa = max(rel + stored, r0), qb = min(rel + c, min(r0 + RASTER_THREADS, n));
               for(uint32_t q = qa; q < qb; q++)
               {
                 const float4 v = queue[q - r0];
@@ -332,6 +340,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
         scanSm[tid] = 0u;
       __threadfence_block();
       __syncthreads();
+#ifdef OIT_EXPERIMENT_NO_CHASE
+      prevHead[tid] = ownTotal;
+#endif
       const uint32_t inBin = atomicAdd(&scanSm[bin], 1u);
       __syncthreads();
       if(warp == 0)
@@ -343,15 +354,32 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       pixOff[scanSm[bin] + inBin] = (uint32_t)tid | (headSm[tid] ? 256u : 0u);
       __syncthreads();
       const uint32_t mine = pixOff[tid];
-      if(mine & 256u)
+      const uint32_t px   = mine & 255u;  // bit 8: a pixel with a list (pixels outside the frame have none)
+#ifdef OIT_EXPERIMENT_NO_CHASE
+      const AbufView av{p.abuf, headSm, (size_t)prevHead[px]};
+#else
+      const AbufView av{p.abuf, headSm, (size_t)TILE_PIX};
+#endif
+      if(p.supersample == 1)
       {
-        const uint32_t px = mine & 255u;  // a pixel with a list (pixels outside the frame have none)
-        const AbufView av{p.abuf, headSm, (size_t)TILE_PIX};
-        fusedCompositePixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)px, 0, tileColorSm + px * S);
+        // the output pixel is the pixel: composite, ROP and resolve in registers, no barrier in between
+        const int gx = tileX0 + (int)(px & (TILE_W - 1)), ly = (int)(px >> TILE_SHIFT);
+        if(gx < p.W && tileY0 + ly < p.H)
+          fusedFinishPixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)px, tileColorSm + px * S, (mine & 256u) != 0 && !(OIT_LL_KNOCKOUT & 1), gx, yLocal0 + ly);
+      }
+      else
+      {
+        if(mine & 256u)
+          fusedCompositePixel<S, OIT_LINKEDLIST>(p, tabs, A, tid, av, (size_t)px, 0, tileColorSm + px * S);
+        __syncthreads();
+        fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
       }
     }
-    __syncthreads();
-    fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
+    else
+    {
+      __syncthreads();
+      fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
+    }
   }
 
   // ---- statistics ----------------------------------------------------------------------------------------------------
