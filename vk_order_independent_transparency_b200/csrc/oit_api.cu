@@ -1,5 +1,6 @@
 // oit_api.cu -- host side of liboit_b200.so: context, device memory, and the frame skeleton of Sample::onRender
 // (oitRender.cpp:28-154) expressed as kernel launches on one CUDA stream.  See include/oit_b200.h for the contract.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -103,6 +104,7 @@ struct OitCtx
   DevBuf       stats[2], tv[2], uboDev[2];
   int          par       = 0;      // the set the next / current frame uses
   bool         pipelined = true;   // OIT_B200_NO_PIPELINE=1: one set, one stream
+  int          experimentFrames = 0;
   cudaStream_t geoStream = nullptr;
   cudaEvent_t  evGeoDone[2]{}, evRasterDone[2]{}, evMain = nullptr;
   bool         rasterRecorded[2]{};
@@ -146,6 +148,10 @@ struct OitCtx
   PeerState* peers     = nullptr;
   bool       peersOpen = false;
   bool       peersUnmapped = false;  // oit_band_peer_disable has run once: the second call frees the exported buffer
+  DevBuf     pushQueue;              // pusher CTAs of the linked-list frame kernel (FrameParams::pushQueue)
+  int        pushers = -1;           // OIT_B200_PUSHERS; default: 16 from four bands up, otherwise 0 = the tile CTAs store to the
+                                     // peers themselves (measured on 8 B200s: colour pass 0.259 -> 0.227 ms with pushers at 8 bands,
+                                     // 0.784 -> 0.818 ms at 2 bands, where the remote traffic is small and the pushers' slots are missed)
   int        sortedBuf[2][2]{};  // [set][draw]
   uint32_t*  hostScalar = nullptr;  // pinned
   OitStats   lastStats{};
@@ -674,7 +680,7 @@ int oit_destroy(OitCtx* c)
   if(!c->finOwned)
     c->fin = DevBuf{};  // a slice of gatherBuf
   for(DevBuf* b : {&c->abuf, &c->aux, &c->spin, &c->adepth, &c->counter, &c->color, &c->depth, &c->wacc, &c->wrev, &c->fin,
-                   &c->tables, &c->rowLocal, &c->stats[0], &c->stats[1], &c->tv[0], &c->tv[1], &c->uboDev[0], &c->uboDev[1], &c->gatherBuf, &c->frame,
+                   &c->tables, &c->rowLocal, &c->pushQueue, &c->stats[0], &c->stats[1], &c->tv[0], &c->tv[1], &c->uboDev[0], &c->uboDev[1], &c->gatherBuf, &c->frame,
                    &c->sphTable, &c->sphUnitPos, &c->sphUnitTri})
     devFree(*b);
   if(c->sceneOwned)
@@ -1105,12 +1111,18 @@ static int issueRaster(OitCtx* c)
   if(exchange)
   {
     // the wait for the other bands' READY comes as late as possible: the clears and the opaque pass absorb the skew
-    c->launches += peerWait(c->peers, PEER_FLAG_READY, stats, c->stream);
+    // pusher CTAs: the linked-list frame kernel without sample shading / super-sampling (oit_raster_ll.cu)
+    const bool push = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading && c->supersample == 1 && c->pushers > 0
+                      && c->pushQueue.p != nullptr;
+    c->fp.pushers   = push ? c->pushers : 0;
+    c->fp.pushQueue = (uint32_t*)c->pushQueue.p;
+    c->launches += peerWait(c->peers, PEER_FLAG_READY, stats, c->stream, push ? c->fp.pushQueue + c->fp.tilesX * c->fp.tileRowsLocal : nullptr);
     record(c, EV_OPAQUE);  // time spent waiting for the other bands is not the colour pass's
   }
   c->fp.peers = (exchange && c->fp.fused) ? peerTable(c->peers) : nullptr;  // the fused kernel stores to every band
   r           = oit_draw_transparent(c);
-  c->fp.peers = nullptr;
+  c->fp.peers   = nullptr;
+  c->fp.pushers = 0;
   if(r != OIT_OK)
     return r;
   if((r = oit_composite(c)) != OIT_OK)
@@ -1123,7 +1135,8 @@ static int issueRaster(OitCtx* c)
       c->launches += peerScatterRows(c->peers, (const uint32_t*)c->fin.p, (int)c->cfg.width, (int)c->localOutH, (int)c->stripRows, c->stream);
     // DONE carries this band's overflow flag: after the wait every band knows whether any band repeats the frame
     c->launches += peerSignal(c->peers, PEER_FLAG_DONE, stats, c->stream);
-    c->launches += peerWait(c->peers, PEER_FLAG_DONE, stats, c->stream);
+    if(getenv("OIT_EXPERIMENT_NO_WAIT") == nullptr)  // (timing experiment: no frame barrier at all -- frames may be torn)
+      c->launches += peerWait(c->peers, PEER_FLAG_DONE, stats, c->stream);
     CUDA_TRY(c, cudaGetLastError());
   }
   // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
@@ -1220,7 +1233,11 @@ static int launchGraphs(OitCtx* c)
   c->launches   = c->graphLaunchCount[set];
   if(c->pipelined)
   {
-    CUDA_TRY(c, cudaGraphLaunch(c->graphExec[set][0], c->geoStream));
+    // (timing experiment OIT_EXPERIMENT_SKIP_GEO=1: after a few frames the geometry half is not launched any more and the
+    // raster halves keep reading the tile lists of the static camera -- what would a free geometry stage buy?)
+    static const bool skipGeo = getenv("OIT_EXPERIMENT_SKIP_GEO") != nullptr;
+    if(!skipGeo || c->experimentFrames++ < 8)
+      CUDA_TRY(c, cudaGraphLaunch(c->graphExec[set][0], c->geoStream));
     CUDA_TRY(c, cudaEventRecord(c->evGeoDone[set], c->geoStream));
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evGeoDone[set], 0));
   }
@@ -1587,6 +1604,18 @@ int oit_band_peer_enable(OitCtx* c, const void* handles, uint32_t count)
   c->peersOpen     = true;
   c->peersUnmapped = false;
   c->graphValid    = false;
+  // the queue of finished tiles for the pusher CTAs (+ its tail counter); entries are consumed and zeroed every frame
+  c->pushers = c->cfg.bandCount >= 4 ? 16 : 0;
+  if(const char* e = getenv("OIT_B200_PUSHERS"))
+    c->pushers = std::max(0, std::min(64, atoi(e)));
+  const size_t words = (size_t)c->fp.tilesX * c->fp.tileRowsLocal + 1;
+  if(c->pushQueue.bytes != words * 4)
+  {
+    const int rq = devAlloc(c, c->pushQueue, words * 4);
+    if(rq != OIT_OK)
+      return rq;
+  }
+  CUDA_TRY(c, cudaMemset(c->pushQueue.p, 0, words * 4));
   return OIT_OK;
 }
 

@@ -327,7 +327,7 @@ __device__ __forceinline__ void fusedCompositePixel(const FrameParams& p, const 
 __device__ __forceinline__ void fusedStorePixel(const FrameParams& p, int gx, int gy, int outW, int ss, uint32_t result)
 {
   p.fin[(size_t)gy * outW + gx] = result;
-  if(p.peers)
+  if(p.peers && p.pushers == 0)
   {
     const int    stripRows = p.stripTileRows * TILE_H / ss;
     const int    strip     = gy / stripRows;

@@ -590,15 +590,18 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
   }
 }
 
-// Launch order of the raster CTAs: heaviest tiles first, so that the light tiles fill the tail of the grid
-// (longest-processing-time-first scheduling).  A counting sort on min(list length, 1023): a histogram pass, then every CTA
+// Launch order of the raster CTAs: empty tiles, then heaviest tiles first, so that the light tiles fill the tail of the grid
+// (longest-processing-time-first scheduling).  A counting sort on min(list length, 1022): a histogram pass, then every CTA
 // scans the 1024 bins for itself and places its tiles with one atomic per tile; the order among tiles of equal weight is
 // arbitrary, which is fine: tiles are independent, the order only affects scheduling.  (bins / cursors: zeroed with the
 // rest of the binning's per-frame state.)
 constexpr int ORDER_BINS = 1024;
 __device__ __forceinline__ uint32_t orderBin(const uint32_t* __restrict__ tileStart, uint32_t t)
 {
-  return (uint32_t)ORDER_BINS - 1u - min(tileStart[t + 1] - tileStart[t], (uint32_t)ORDER_BINS - 1u);  // bin 0 = heaviest
+  // bin 0 = the empty tiles (their CTAs only write the clear colour: over in no time, and in split-frame mode their pixels
+  // travel to the other bands while the heavy tiles are rasterised instead of in a burst at the end), bin 1 = the heaviest
+  const uint32_t len = tileStart[t + 1] - tileStart[t];
+  return len == 0u ? 0u : (uint32_t)ORDER_BINS - 1u - min(len, (uint32_t)ORDER_BINS - 2u);
 }
 __global__ void __launch_bounds__(256) k_tile_hist(const uint32_t* __restrict__ tileStart, uint32_t numTiles, uint32_t* __restrict__ bins)
 {

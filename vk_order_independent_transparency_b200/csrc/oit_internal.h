@@ -146,6 +146,11 @@ struct FrameParams
   uint16_t*            wrev;
   uint32_t*            fin;
   const PeerTable*     peers;   // split frame over peer memory: every band's whole-frame buffer (nullptr = off)
+  // ... with pusher CTAs (oit_raster_ll.cu): the tile CTAs only write `fin` and publish the finished tile in pushQueue; the
+  // first `pushers` CTAs of the grid copy finished tiles into every band's frame with 128-bit stores, so that NVLink
+  // back-pressure stalls THEM and not the SMs that rasterise.  0 = the tile's own threads store to the peers.
+  uint32_t*            pushQueue;  // [numLocalTiles] tile + 1 in completion order (0 = not yet), [numLocalTiles] = the tail counter
+  int                  pushers;
   const float*         tables;  // the SrgbTables image (oit_device.cuh), SRGB_TABLE_BYTES
   unsigned long long*  stats;
   // geometry
@@ -235,7 +240,7 @@ void             peerDestroy(PeerState* ps);
 uint32_t*        peerFrame(PeerState* ps);
 const PeerTable* peerTable(PeerState* ps);
 int              peerSignal(PeerState* ps, int phase, const unsigned long long* stats, cudaStream_t s);
-int              peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s);
+int              peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s, uint32_t* zeroWord = nullptr);
 int peerScatterRows(PeerState* ps, const uint32_t* fin, int W, int localRows, int stripRows, cudaStream_t s);
 
 int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);

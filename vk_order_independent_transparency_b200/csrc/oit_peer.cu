@@ -164,8 +164,11 @@ __global__ void __launch_bounds__(32) k_peer_signal(const PeerTable* __restrict_
 }
 
 // one thread per band: spins until band b's flag in THIS band's buffer reaches the frame being rendered
-__global__ void __launch_bounds__(32) k_peer_wait(const PeerTable* __restrict__ t, int world, int rank, int phase, unsigned long long* stats)
+__global__ void __launch_bounds__(32) k_peer_wait(const PeerTable* __restrict__ t, int world, int rank, int phase, unsigned long long* stats,
+                                                   uint32_t* zeroWord)
 {
+  if(zeroWord && threadIdx.x == 0)
+    *zeroWord = 0u;  // the tail of the pusher queue, reset before the frame kernel starts
   const int      b     = threadIdx.x;
   uint32_t*      local = t->flags[rank];
   const uint32_t seq   = local[PEER_FLAG_SEQ] + 1u;
@@ -203,9 +206,9 @@ int peerSignal(PeerState* ps, int phase, const unsigned long long* stats, cudaSt
   return 1;
 }
 
-int peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s)
+int peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s, uint32_t* zeroWord)
 {
-  k_peer_wait<<<1, 32, 0, s>>>(ps->table, ps->world, ps->rank, phase, stats);
+  k_peer_wait<<<1, 32, 0, s>>>(ps->table, ps->world, ps->rank, phase, stats, zeroWord);
   return 1;
 }
 

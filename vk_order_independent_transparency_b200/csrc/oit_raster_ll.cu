@@ -31,22 +31,134 @@ namespace oit {
 
 constexpr int LL_CHUNK     = 128;  // triangles staged per chunk = bits of a pixel's per-batch triangle set
 constexpr int LL_IPT       = ITEMS_PER_THREAD;
-constexpr int LL_BATCH     = RASTER_THREADS * LL_IPT;
-#ifndef OIT_LL_MIN_BLOCKS
-#define OIT_LL_MIN_BLOCKS 5
+constexpr int LL_ROUND     = RASTER_THREADS * LL_IPT;  // candidates tested per coverage round
+// Per sample count: coverage rounds per batch (a batch = ROUNDS * 1024 candidates between two allocation phases; its lists
+// take ROUNDS * 8 KB of shared memory) and resident CTAs per SM (5: 48 registers; 4: 64 registers, no spills).  Measured on
+// B200: the 8-sample instance runs best with longer batches at 4 CTAs, the others with the short batch at 5.
+#ifndef OIT_LL_ROUNDS_S8
+#define OIT_LL_ROUNDS_S8 2
 #endif
+#ifndef OIT_LL_MINB_S8
+#define OIT_LL_MINB_S8 4
+#endif
+#ifndef OIT_LL_ROUNDS_S4
+#define OIT_LL_ROUNDS_S4 2
+#endif
+#ifndef OIT_LL_MINB_S4
+#define OIT_LL_MINB_S4 5
+#endif
+#ifndef OIT_LL_ROUNDS_S1
+#define OIT_LL_ROUNDS_S1 2
+#endif
+#ifndef OIT_LL_MINB_S1
+#define OIT_LL_MINB_S1 5
+#endif
+__host__ __device__ constexpr int llRounds(int S) { return S == 8 ? OIT_LL_ROUNDS_S8 : (S == 4 ? OIT_LL_ROUNDS_S4 : OIT_LL_ROUNDS_S1); }
+__host__ __device__ constexpr int llMinBlocks(int S) { return S == 8 ? OIT_LL_MINB_S8 : (S == 4 ? OIT_LL_MINB_S4 : OIT_LL_MINB_S1); }
 #ifndef OIT_LL_KNOCKOUT
 #define OIT_LL_KNOCKOUT 0  // timing experiments only (tools/build_variants.sh): 1 = no composite, 2 = no shading, 4 = no node store
 #endif
 
-template <int S>
-__global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll(const FrameParams p)
+// ---- split frame with pusher CTAs -------------------------------------------------------------------------------------------
+// The tile CTAs write their resolved pixels to `fin` and append the tile to a queue (completion order); the first
+// p.pushers CTAs of the grid -- dispatched first, so resident for the whole kernel -- take queue slots round robin, one warp
+// per tile, and copy the tile's 16 rows x 64 bytes into EVERY band's whole-frame buffer with 128-bit stores over NVLink.
+// Compute and exchange stay one kernel, but the remote stores (7 x 4 bytes per pixel at 8 bands) are issued by a few
+// warps whose only job that is: NVLink back-pressure stalls them instead of the load/store units of the rasterising SMs
+// (per-pixel stores from the tile CTAs cost +28 % of the colour pass at 8 bands), and the transfers are 64-byte segments.
+__device__ __forceinline__ uint32_t ldAcquireGpu(const uint32_t* a)
 {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stReleaseGpu(uint32_t* a, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pushTimerNs()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// a tile CTA is done with its tile: every thread's stores to `fin` are ordered before the queue entry
+__device__ __forceinline__ void publishTile(const FrameParams& p, uint32_t tile)
+{
+  if(p.pushers == 0)
+    return;
+  __threadfence();
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    const uint32_t numTiles = (uint32_t)(p.tilesX * p.tileRowsLocal);
+    const uint32_t slot     = atomicAdd(p.pushQueue + numTiles, 1u);
+    stReleaseGpu(p.pushQueue + slot, tile + 1u);
+  }
+}
+
+__device__ __noinline__ void pushTiles(const FrameParams p)
+{
+  const int      lane = threadIdx.x & 31, warpsPerCta = RASTER_THREADS / 32;
+  const uint32_t numTiles = (uint32_t)(p.tilesX * p.tileRowsLocal);
+  const uint32_t nWarps = (uint32_t)p.pushers * warpsPerCta, myWarp = blockIdx.x * warpsPerCta + (threadIdx.x >> 5);
+  const int      stripRows = p.stripTileRows * TILE_H;
+  const uint4*   fin4 = reinterpret_cast<const uint4*>(p.fin);
+  const int      quadsPerRow = p.W / 4;
+  for(uint32_t slot = myWarp; slot < numTiles; slot += nWarps)
+  {
+    uint32_t v = 0;
+    if(lane == 0)
+    {
+      const unsigned long long t0 = pushTimerNs();
+      while((v = ldAcquireGpu(p.pushQueue + slot)) == 0u)
+      {
+        if(pushTimerNs() - t0 > 2000000000ull)
+        {
+          atomicAdd(p.stats + STAT_PEER_TIMEOUT, 1ull);  // (cannot happen: every tile CTA publishes; reported, not hung)
+          break;
+        }
+        __nanosleep(64);
+      }
+      p.pushQueue[slot] = 0u;  // ready for the next frame
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if(v == 0u)
+      return;
+    const uint32_t tile = v - 1u;
+    const int      rl = (int)(tile / p.tilesX), tx = (int)(tile - rl * p.tilesX);
+#pragma unroll
+    for(int q = lane; q < TILE_H * (TILE_W / 4); q += 32)
+    {
+      const int row = q / (TILE_W / 4), seg = q - row * (TILE_W / 4);
+      const int yl = rl * TILE_H + row, xq = tx * (TILE_W / 4) + seg;
+      if(yl < p.localH && xq < quadsPerRow)
+      {
+        const uint4  px    = __ldcg(fin4 + (size_t)yl * quadsPerRow + xq);
+        const int    strip = yl / stripRows;
+        const size_t o     = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (yl - strip * stripRows)) * quadsPerRow + xq;
+        for(int b = 0; b < p.bandCount; b++)
+          reinterpret_cast<uint4*>(p.peers->frame[b])[o] = px;
+      }
+    }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(RASTER_THREADS, llMinBlocks(S)) k_raster_ll(const FrameParams p)
+{
+  if(p.pushers && blockIdx.x < (unsigned)p.pushers)
+  {
+    pushTiles(p);
+    return;
+  }
+  constexpr int LL_BATCH = LL_ROUND * llRounds(S);
   static_assert(RASTER_THREADS == TILE_PIX, "phase B maps one thread to one pixel of the tile");
   // per-chunk / per-batch structures; dead once the tile's list has been walked, when the fused composite reuses the space
   constexpr size_t SLOT_BYTES = sizeof(TriSlot) * LL_CHUNK;
   constexpr size_t SET_BYTES  = sizeof(uint4) * TILE_PIX * 2;        // per-pixel triangle sets of two consecutive batches
-  constexpr size_t LIST_BYTES = sizeof(uint32_t) * LL_BATCH * 2;     // compact fragment lists of two consecutive batches
+  constexpr size_t LIST_BYTES = sizeof(uint32_t) * LL_BATCH * 2;      // compact fragment lists of two consecutive batches
   constexpr size_t WORK_BYTES = SLOT_BYTES + SET_BYTES + LIST_BYTES;
   constexpr size_t SCRATCH_BYTES = WORK_BYTES > sizeof(FusedArrays) ? WORK_BYTES : sizeof(FusedArrays);
   static_assert(SLOT_BYTES % 16 == 0, "alignment of the sets");
@@ -67,7 +179,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
   uint32_t* lists   = reinterpret_cast<uint32_t*>(scratch + SLOT_BYTES + SET_BYTES);
 
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = p.tileOrder[blockIdx.x];  // launch order: longest lists first
+  const uint32_t tile = p.tileOrder[blockIdx.x - p.pushers];  // launch order: longest lists first
   const uint32_t listBegin = p.tileStart[tile], listEnd = p.tileStart[tile + 1];
   const bool     fused = p.fused != 0;
   if(listBegin == listEnd && !fused)
@@ -92,6 +204,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       if(emptyTile)
       {
         fusedClearTile(p, tileX0, yLocal0, tid);
+        publishTile(p, tile);
         return;
       }
       const uint4 cc = make_uint4(p.clearColor, p.clearColor, p.clearColor, p.clearColor);
@@ -188,9 +301,16 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       // ---- A: coverage of LL_IPT consecutive candidates of one triangle; compact list of the covered ones --------------------
       if(tid == 0)
         sCount[par ^ 1u] = 0u;
-      uint32_t recs[LL_IPT];
-      coverCandidates<S, LL_CHUNK>(p, slots, itemStart, k0 + tid * LL_IPT, total, tileX0, tileY0, yLocal0, setWords, recs);
-      appendCovered(recs, &sCount[par], list);
+#pragma unroll 1
+      for(int round = 0; round < llRounds(S); round++)
+      {
+        const uint32_t k = k0 + round * LL_ROUND + tid * LL_IPT;
+        if(round > 0 && k0 + round * LL_ROUND >= total)
+          break;
+        uint32_t recs[LL_IPT];
+        coverCandidates<S, LL_CHUNK>(p, slots, itemStart, k, total, tileX0, tileY0, yLocal0, setWords, recs);
+        appendCovered(recs, &sCount[par], list);
+      }
       __syncthreads();  // (1)
 
       // ---- B: thread = pixel.  Fragment count of the pixel, its node range, the new head ---------------------------------------
@@ -380,6 +500,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
       __syncthreads();
       fusedResolveTile<S>(p, tabs, tileColorSm, tileX0, yLocal0, tid);
     }
+    publishTile(p, tile);
   }
 
   // ---- statistics ----------------------------------------------------------------------------------------------------
@@ -396,19 +517,37 @@ __global__ void __launch_bounds__(RASTER_THREADS, OIT_LL_MIN_BLOCKS) k_raster_ll
   }
 }
 
+template <int S>
+static void launchLL(const FrameParams& p, unsigned grid, cudaStream_t s)
+{
+  const size_t dyn = p.fused ? (size_t)TILE_PIX * S * sizeof(uint32_t) : 0;
+  // static + dynamic shared memory can exceed 48 KB: opt in once per device (function attributes are per device, and
+  // contexts of several GPUs may live in one process)
+  static bool configured[64] = {};
+  int         dev            = 0;
+  cudaGetDevice(&dev);
+  if(dev < 0 || dev >= 64 || !configured[dev])
+  {
+    if(cudaFuncSetAttribute(k_raster_ll<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TILE_PIX * S * sizeof(uint32_t))) != cudaSuccess)
+      return;  // stays in cudaGetLastError(), which every stage entry point checks after its launches
+    if(dev >= 0 && dev < 64)
+      configured[dev] = true;
+  }
+  k_raster_ll<S><<<grid + (unsigned)p.pushers, RASTER_THREADS, dyn, s>>>(p);
+}
+
 // The linked-list colour pass without sample shading (no AA, MSAA with coverage masks, super-sampling)
 int launchRasterLinkedList(const FrameParams& p, cudaStream_t s)
 {
   const unsigned grid = (unsigned)(p.tilesX * p.tileRowsLocal);
   if(grid == 0)
     return 0;
-  const size_t dyn = p.fused ? (size_t)TILE_PIX * p.msaa * sizeof(uint32_t) : 0;
   if(p.msaa == 1)
-    k_raster_ll<1><<<grid, RASTER_THREADS, dyn, s>>>(p);
+    launchLL<1>(p, grid, s);
   else if(p.msaa == 4)
-    k_raster_ll<4><<<grid, RASTER_THREADS, dyn, s>>>(p);
+    launchLL<4>(p, grid, s);
   else
-    k_raster_ll<8><<<grid, RASTER_THREADS, dyn, s>>>(p);
+    launchLL<8>(p, grid, s);
   return 1;
 }
 
