@@ -34,7 +34,8 @@ WORKLOADS = {
 TECH_TABLE = [(a, 0) for a in range(7)]  # per-technique table at 3840x2160, no AA, default parameters
 
 
-KERNEL_SOURCES = ["oit_raster.cu", "oit_fragment.cuh", "oit_fused.cuh", "oit_device.cuh", "oit_internal.h", "oit_clip.cuh"]
+KERNEL_SOURCES = ["oit_raster_ll.cu", "oit_raster_q.cu", "oit_raster.cu", "oit_raster_common.cuh", "oit_fragment.cuh", "oit_fused.cuh", "oit_device.cuh",
+                  "oit_internal.h", "oit_clip.cuh"]
 
 
 def kernel_source_hash():
@@ -109,6 +110,17 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.path)
+        if not sm:
+            # the timed region was shorter than the polling period: one direct query right after it (the GPU is still warm)
+            try:
+                f = [x.strip() for x in subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                                       capture_output=True, text=True, timeout=10).stdout.strip().split(",")]
+                sm, mx = [float(f[1])], [float(f[2])]
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
         if sm:
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
         return out
@@ -210,15 +222,17 @@ def run_ours(args):
         s.readColor(hfinal.numpy().view(np.uint32))                      # D2H of the step's result
 
     def timed(step, steps, warmup, sample_clocks=False):
+        # (the clock sampler polls every 20 ms: it starts before the warm-up so that a short timed region -- 40 frames of
+        # 0.35 ms at 8 GPUs -- still falls between samples taken under load; samples of the warm-up are load samples too)
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
         for _ in range(warmup):
             step()
         s.synchronize()   # oit_render is asynchronous: completes the warm-up frames (and their one-off buffer growth)
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage = {"geometry": 0.0, "clear": 0.0, "color": 0.0, "composite": 0.0, "resolve": 0.0, "opaque": 0.0}
+        stage = {"geometry": 0.0, "clear": 0.0, "color": 0.0, "composite": 0.0, "resolve": 0.0, "opaque": 0.0, "exchange_wait": 0.0}
         launches = 0
         e0.record(stream)
         t0 = time.perf_counter()
@@ -233,7 +247,8 @@ def run_ours(args):
         for _ in range(min(steps, 5)):
             step()
             sst = s.stats()
-            for k, n in (("geometry", "msGeometry"), ("clear", "msClear"), ("color", "msColor"), ("composite", "msComposite"), ("resolve", "msResolve"), ("opaque", "msOpaque")):
+            for k, n in (("geometry", "msGeometry"), ("clear", "msClear"), ("color", "msColor"), ("composite", "msComposite"), ("resolve", "msResolve"),
+                         ("opaque", "msOpaque"), ("exchange_wait", "msExchangeWait")):
                 stage[k] += sst[n] / min(steps, 5) * steps
         launches = sst["kernelLaunches"] * steps
         t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
@@ -257,6 +272,15 @@ def run_ours(args):
         okt = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_ok = bool(okt.item())
+    # split frame: colour-pass time, wait time and fragment count of EVERY band (rank order)
+    per_band = None
+    if world > 1:
+        mine = torch.tensor([stage_ms["color"], stage_ms["exchange_wait"], stage_ms["geometry"], float(last["fragments"])], dtype=torch.float64, device=dev)
+        allb = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        per_band = {"color_ms": [round(t[0].item(), 4) for t in allb], "exchange_wait_ms": [round(t[1].item(), 4) for t in allb],
+                    "geometry_ms": [round(t[2].item(), 4) for t in allb], "fragments": [int(t[3].item()) for t in allb],
+                    "note": "per-stage times come from frames rendered one at a time after the timed loop (library events); the wait is READY + DONE"}
     F_local = last["fragments"]
     Ft = torch.tensor([F_local, last["fragmentsStored"], last["fragmentsTail"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -313,7 +337,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {desc}", "fragments_per_frame": F, "fragments_stored": Fst, "fragments_tail": Ftb,
                        "width": W, "height": H, "parallelism": f"split-frame x{world}, {args.strip_rows}-row interleaved strips" if world > 1 else "single GPU",
                        "band_gather": None if world == 1 else ("torch.distributed all_gather" if band_gather is not None else exchange),
-                       "band_gather_verified": gather_ok,
+                       "band_gather_verified": gather_ok, "bands": per_band,
                        "l2_policy": "working set (A-buffer + colour samples) is larger than L2; no explicit flush"},
             "ms_per_frame": frame_ms, "wall_ms_per_frame": wall_total / args.steps, "stages": per_stage, "gpu_launches": int(launches),
             "e2e": {"value": F / (e2e_ms * 1e-3), "unit": "fragments/s", "ms_per_step": e2e_ms,

@@ -130,6 +130,7 @@ typedef struct OitStats
   float    msComposite;        /* <Tech>Composite */
   float    msResolve;          /* copyOffscreenToBackBuffer */
   float    msFrame;            /* whole oit_render on the device */
+  float    msExchangeWait;     /* split frame over peer memory: time this band waited for the other bands (READY + DONE rounds) */
 } OitStats;
 
 /* device/host buffers addressable through oit_download / oit_upload / oit_device_ptr */

@@ -66,7 +66,8 @@ class OitStats(C.Structure):
                                           "trianglesDrawn", "trianglesRejected", "llCounter", "tilePairs",
                                           "kernelLaunches")] + \
                [(n, C.c_float) for n in ("msGeometry", "msClear", "msOpaque", "msColor", "msComposite", "msResolve",
-                                         "msFrame")]
+                                         "msFrame", "msExchangeWait")]
+assert C.sizeof(OitStats) == 104
 
 
 assert C.sizeof(SceneData) == 224

@@ -1442,6 +1442,7 @@ int oit_get_stats(OitCtx* c, OitStats* out)
   s.msResolve   = ms(EV_COMPOSITE, EV_RESOLVE);
   // the two halves of a frame run on two streams (the next frame's geometry overlaps this frame's raster): their sum
   s.msFrame     = s.msGeometry + ms(EV_RASTER_START, EV_RESOLVE);
+  s.msExchangeWait = (float)((double)h[STAT_WAIT_NS] * 1e-6);
   c->lastStats  = s;
   *out          = s;
   return OIT_OK;

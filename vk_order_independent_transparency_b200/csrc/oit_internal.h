@@ -78,6 +78,7 @@ enum StatSlot
   STAT_INTERNAL,      // a look-back chain of the binning gave up (cannot happen; reported instead of hanging the GPU)
   STAT_OVERFLOW_ANY,  // split frame: SOME band raised STAT_OVERFLOW for this frame (carried by the exchange itself), so that
                       // every band takes the same decision to render the frame again
+  STAT_WAIT_NS,       // split frame: nanoseconds this band spent in the READY and DONE waits of the frame
   NUM_STAT_SLOTS = 12
 };
 

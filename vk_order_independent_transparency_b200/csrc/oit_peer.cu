@@ -172,9 +172,10 @@ __global__ void __launch_bounds__(32) k_peer_wait(const PeerTable* __restrict__ 
   const int      b     = threadIdx.x;
   uint32_t*      local = t->flags[rank];
   const uint32_t seq   = local[PEER_FLAG_SEQ] + 1u;
+  const unsigned long long tStart = globalTimerNs();
   if(b < world)
   {
-    const unsigned long long t0 = globalTimerNs();
+    const unsigned long long t0 = tStart;
     while((int32_t)(ldAcquireSys(local + phase + b) - seq) < 0)
     {
       if(globalTimerNs() - t0 > PEER_TIMEOUT_NS)
@@ -187,6 +188,8 @@ __global__ void __launch_bounds__(32) k_peer_wait(const PeerTable* __restrict__ 
   }
   __syncwarp();
   __threadfence_system();
+  if(b == 0)
+    stats[STAT_WAIT_NS] += globalTimerNs() - tStart;  // (after the __syncwarp: the slowest band's flag has arrived)
   if(phase == PEER_FLAG_DONE)
   {
     // the overflow flags travelled with DONE (written before the flag's release store, read after its acquire load)
