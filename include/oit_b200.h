@@ -233,12 +233,17 @@ int oit_band_gather_unique_id(void* id128);
 int oit_enable_band_gather(OitCtx* ctx, const void* id128);
 
 /* ---- split frame over NVLink peer memory (preferred; same contexts as above, no reference counterpart) ----------------
-   Every band owns a whole-frame buffer (OIT_BUF_FRAME).  oit_band_peer_export allocates it and returns its CUDA IPC handle
-   (64 bytes); the host gathers the handles of all bands in band order (any transport) and passes them to
-   oit_band_peer_enable, which maps the other bands' buffers.  From then on the frame kernel of oit_render stores every
-   resolved pixel straight into ALL bands' frame buffers while it renders (no collective after the frame), and two flag
-   rounds per frame (device-side sequence numbers, part of the frame graph) keep the bands in step; OIT_BUF_FRAME holds
-   the whole frame on every band once the frame is complete (oit_synchronize).  Every band must call oit_render the same number of times.
+   Every band owns two whole-frame buffers (frames alternate between them; OIT_BUF_FRAME is the one that holds the latest
+   completed frame).  oit_band_peer_export allocates them and returns their CUDA IPC handle (64 bytes); the host gathers the
+   handles of all bands in band order (any transport) and passes them to oit_band_peer_enable, which maps the other bands'
+   buffers.  From then on the frame kernel of oit_render stores its resolved pixels straight into ALL bands' frame buffers
+   while it renders (no collective after the frame; from four bands up a few CTAs of the frame kernel do nothing but push
+   finished tiles over NVLink), and two flag rounds per frame (device-side sequence numbers, part of the frame graph) keep
+   the bands in step ONE FRAME LATE, so that a stream of oit_render calls never idles at a barrier; the calls that complete a
+   frame (oit_synchronize, oit_download, oit_get_stats, ...) wait until every band's strips of the latest frame have arrived.
+   OIT_BUF_FRAME / oit_device_ptr(OIT_BUF_FRAME) then is the whole frame on every band, valid until the next oit_render
+   (ask for the pointer again after every completed frame: it alternates).  Every band must call oit_render the same number
+   of times.
    Tear-down: all bands finish rendering, host barrier, oit_band_peer_disable on every band (unmaps the other bands'
    buffers, frees nothing), host barrier, oit_destroy -- or a second oit_band_peer_disable, which releases the exported
    buffer and leaves the context usable (e.g. to fall back to the NCCL gather when some band could not map its peers).

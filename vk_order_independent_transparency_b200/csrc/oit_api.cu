@@ -147,6 +147,7 @@ struct OitCtx
   int    sphSubdiv = 0;
   PeerState* peers     = nullptr;
   bool       peersOpen = false;
+  unsigned   peerSeq   = 0;  // frames issued with the exchange: the latest one is in frame buffer peerSeq & 1
   bool       peersUnmapped = false;  // oit_band_peer_disable has run once: the second call frees the exported buffer
   DevBuf     pushQueue;              // pusher CTAs of the linked-list frame kernel (FrameParams::pushQueue)
   int        pushers = -1;           // OIT_B200_PUSHERS; default: 16 from four bands up, otherwise 0 = the tile CTAs store to the
@@ -1004,7 +1005,12 @@ int oit_begin_frame(OitCtx* c)
   }
   record(c, EV_RASTER_START);
   // clearTransparent* + colour/depth clear
-  c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream);
+  {
+    // the fused linked-list frame kernel starts every list empty by itself (no imgAux clear), and in split-frame mode the
+    // first node of the exchange (k_peer_frame_begin) resets the node counter
+    const bool leanLL = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading;
+    c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream, leanLL, leanLL && c->peers && c->peersOpen);
+  }
   record(c, EV_CLEAR);
   CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
@@ -1062,7 +1068,8 @@ int oit_composite(OitCtx* c)
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->fp.fused)
     c->launches += launchComposite(c->fp, (int)c->cfg.algorithm, c->stream);
-  record(c, EV_COMPOSITE);
+  if(!c->fp.fused)  // (fused frame: no stage, and an event-record node costs ~2.6 us of every replayed frame)
+    record(c, EV_COMPOSITE);
   CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
 }
@@ -1075,7 +1082,8 @@ int oit_resolve(OitCtx* c)
   CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if(!c->fp.fused)
     c->launches += launchResolve(c->fp, c->supersample, (int)c->cfg.width, (int)c->localOutH, c->stream);
-  record(c, EV_RESOLVE);
+  if(!c->fp.fused)
+    record(c, EV_RESOLVE);
   CUDA_TRY(c, cudaGetLastError());
   return OIT_OK;
 }
@@ -1088,13 +1096,6 @@ int oit_synchronize(OitCtx* c)
   if(const int fr = finishFrame(c); fr != OIT_OK)  // completes a frame oit_render left in flight, then the stream is idle
     return fr;
   return OIT_OK;
-}
-
-// "my frame buffer may be overwritten": the first thing a band says about a frame (split frame over peer memory)
-static void issueReadySignal(OitCtx* c)
-{
-  if(c->peers && c->peersOpen)
-    c->launches += peerSignal(c->peers, PEER_FLAG_READY, (const unsigned long long*)c->stats[c->par].p, c->stream);
 }
 
 // The raster half of one frame, asynchronously on the main stream: clears, opaque pass, colour pass(es), composite, resolve,
@@ -1110,13 +1111,15 @@ static int issueRaster(OitCtx* c)
     return r;
   if(exchange)
   {
-    // the wait for the other bands' READY comes as late as possible: the clears and the opaque pass absorb the skew
     // pusher CTAs: the linked-list frame kernel without sample shading / super-sampling (oit_raster_ll.cu)
-    const bool push = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading && c->supersample == 1 && c->pushers > 0
-                      && c->pushQueue.p != nullptr;
-    c->fp.pushers   = push ? c->pushers : 0;
-    c->fp.pushQueue = (uint32_t*)c->pushQueue.p;
-    c->launches += peerWait(c->peers, PEER_FLAG_READY, stats, c->stream, push ? c->fp.pushQueue + c->fp.tilesX * c->fp.tileRowsLocal : nullptr);
+    const bool leanLL = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading;
+    const bool push   = leanLL && c->supersample == 1 && c->pushers > 0 && c->pushQueue.p != nullptr;
+    c->fp.pushers     = push ? c->pushers : 0;
+    c->fp.pushQueue   = (uint32_t*)c->pushQueue.p;
+    // the exchange's first node comes as late as possible (the clears and the opaque pass absorb what skew there is): it
+    // allows the NEXT frame into this band's other buffer and checks that every band allows this one
+    c->launches += peerFrameBegin(c->peers, stats, leanLL ? c->fp.counter : nullptr,
+                                  push ? c->fp.pushQueue + c->fp.tilesX * c->fp.tileRowsLocal : nullptr, c->stream);
     record(c, EV_OPAQUE);  // time spent waiting for the other bands is not the colour pass's
   }
   c->fp.peers = (exchange && c->fp.fused) ? peerTable(c->peers) : nullptr;  // the fused kernel stores to every band
@@ -1133,11 +1136,12 @@ static int issueRaster(OitCtx* c)
   {
     if(!c->fp.fused)
       c->launches += peerScatterRows(c->peers, (const uint32_t*)c->fin.p, (int)c->cfg.width, (int)c->localOutH, (int)c->stripRows, c->stream);
-    // DONE carries this band's overflow flag: after the wait every band knows whether any band repeats the frame
-    c->launches += peerSignal(c->peers, PEER_FLAG_DONE, stats, c->stream);
-    if(getenv("OIT_EXPERIMENT_NO_WAIT") == nullptr)  // (timing experiment: no frame barrier at all -- frames may be torn)
-      c->launches += peerWait(c->peers, PEER_FLAG_DONE, stats, c->stream);
+    // last node: DONE (with this band's overflow flag), the wait for the PREVIOUS frame's DONE, the statistics mirror
+    c->launches += peerFrameEnd(c->peers, stats, c->hostMirror, NUM_STAT_SLOTS,
+                                (c->bins[c->par][0].pairInfo && c->drawTris[0] > 0) ? c->bins[c->par][0].pairInfo : nullptr,
+                                (c->bins[c->par][1].pairInfo && c->drawTris[1] > 0) ? c->bins[c->par][1].pairInfo : nullptr, c->stream);
     CUDA_TRY(c, cudaGetLastError());
+    return OIT_OK;
   }
   // split frame: ONE all-gather of the resolved strips over NVLink + the row interleave, still on the same stream
   if(c->gather)
@@ -1172,14 +1176,12 @@ static int issueFrameStreams(OitCtx* c)
       return r;
     CUDA_TRY(c, cudaEventRecord(c->evGeoDone[c->par], c->geoStream));
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->evGeoDone[c->par], 0));
-    issueReadySignal(c);
     if((r = issueRaster(c)) != OIT_OK)
       return r;
     CUDA_TRY(c, cudaEventRecord(c->evRasterDone[c->par], c->stream));
     c->rasterRecorded[c->par] = true;
     return OIT_OK;
   }
-  issueReadySignal(c);
   if((r = issueGeometry(c, c->stream)) != OIT_OK)
     return r;
   return issueRaster(c);
@@ -1211,7 +1213,6 @@ static int buildGraphs(OitCtx* c)
   e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
   if(e == cudaSuccess)
   {
-    issueReadySignal(c);
     if(!c->pipelined)
       r = issueGeometry(c, c->stream);
     if(r == OIT_OK)
@@ -1301,7 +1302,11 @@ static int enqueueFrame(OitCtx* c)
     c->fp.fused  = 0;
     c->fp.onChip = 0;
     if(!retry)
+    {
+      if(r == OIT_OK && c->peers && c->peersOpen)
+        c->peerSeq++;  // (the device counts the same frames: k_peer_frame_end)
       return r;
+    }
   }
   return r;
 }
@@ -1322,6 +1327,13 @@ static int finishFrame(OitCtx* c)
   {
     // (every raster half waits for its geometry half: the main stream drains last)
     CUDA_TRY(c, cudaStreamSynchronize(c->geoStream));
+    if(c->peers && c->peersOpen)
+    {
+      // split frame over peer memory: the bands agree on frame boundaries one frame late, so the LATEST frame is completed
+      // here -- every band's strips are in this band's buffer, and every band's overflow flag is known
+      peerFrameFlush(c->peers, (unsigned long long*)c->stats[c->par].p, c->hostMirror, c->stream);
+      c->frame.p = peerFrame(c->peers, c->peerSeq);
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->framePending = false;
     bool grown      = false;
@@ -1441,7 +1453,7 @@ int oit_get_stats(OitCtx* c, OitStats* out)
   s.msComposite = ms(EV_COLOR, EV_COMPOSITE);
   s.msResolve   = ms(EV_COMPOSITE, EV_RESOLVE);
   // the two halves of a frame run on two streams (the next frame's geometry overlaps this frame's raster): their sum
-  s.msFrame     = s.msGeometry + ms(EV_RASTER_START, EV_RESOLVE);
+  s.msFrame     = s.msGeometry + ms(EV_RASTER_START, c->evRecorded[EV_RESOLVE] ? EV_RESOLVE : EV_COLOR);
   s.msExchangeWait = (float)((double)h[STAT_WAIT_NS] * 1e-6);
   c->lastStats  = s;
   *out          = s;
@@ -1580,10 +1592,11 @@ int oit_band_peer_export(OitCtx* c, void* handle64)
   c->peers           = peerCreate((int)c->cfg.bandIndex, (int)c->cfg.bandCount, bytes, handle64, c->error);
   c->peersOpen       = false;
   c->peersUnmapped   = false;
+  c->peerSeq         = 0;  // (the new buffers' device-side frame counter starts at 0 too)
   if(!c->peers)
     return OIT_ERR_UNSUPPORTED;
   devFree(c->frame);
-  c->frame.p     = peerFrame(c->peers);
+  c->frame.p     = peerFrame(c->peers, c->peerSeq);
   c->frame.bytes = bytes;
   return OIT_OK;
 }

@@ -36,7 +36,7 @@ static int fill32(void* dst, size_t nWords, uint32_t value, cudaStream_t s)
   return 1;
 }
 
-int launchClears(const FrameParams& p, int algorithm, cudaStream_t s)
+int launchClears(const FrameParams& p, int algorithm, cudaStream_t s, bool skipListHeads, bool skipCounter)
 {
   const size_t P        = (size_t)p.W * p.localH;
   const size_t auxWords = P * p.layers;
@@ -45,8 +45,10 @@ int launchClears(const FrameParams& p, int algorithm, cudaStream_t s)
   {
     case OIT_SIMPLE: n += fill32(p.aux, auxWords, 0u, s); break;
     case OIT_LINKEDLIST:
-      n += fill32(p.aux, auxWords, 0u, s);
-      n += fill32(p.counter, 1, 0u, s);
+      if(!skipListHeads)
+        n += fill32(p.aux, auxWords, 0u, s);
+      if(!skipCounter)
+        n += fill32(p.counter, 1, 0u, s);
       break;
     case OIT_LOOP:
       // only the depth half of every sample block (oitRender.cpp:252-261)

@@ -332,8 +332,9 @@ __device__ __forceinline__ void fusedStorePixel(const FrameParams& p, int gx, in
     const int    stripRows = p.stripTileRows * TILE_H / ss;
     const int    strip     = gy / stripRows;
     const size_t o         = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (gy - strip * stripRows)) * outW + gx;
+    uint32_t* const* frames = peerFramesOfRunningFrame(p.peers, p.bandIndex);
     for(int b = 0; b < p.bandCount; b++)
-      p.peers->frame[b][o] = result;
+      frames[b][o] = result;
   }
 }
 

@@ -85,17 +85,25 @@ enum StatSlot
 // Split frame over NVLink peer memory (oit_peer.cu): band b's resolved pixels are stored straight into the whole-frame
 // buffer of every band (its own included) by the kernel that produces them.
 constexpr int PEER_MAX       = 16;
-constexpr int PEER_FLAG_READY = 0;             // flags[READY + b] = n: band b no longer reads frame n - 1 of ITS buffer
-constexpr int PEER_FLAG_DONE  = PEER_MAX;      // flags[DONE + b]  = n: band b's strips of frame n are in THIS buffer
-constexpr int PEER_FLAG_SEQ   = 2 * PEER_MAX;  // frames completed by this band (local use)
-constexpr int PEER_FLAG_OVF   = 2 * PEER_MAX + 1;  // flags[OVF + b] = n: band b's frame n overflowed a pair / clip buffer
-constexpr int PEER_FLAG_WORDS = 64;
-static_assert(PEER_FLAG_OVF + PEER_MAX <= PEER_FLAG_WORDS, "peer flag page");
+// Every band has TWO whole-frame buffers; frame n of the context goes to buffer n & 1 of every band, so that the bands only
+// have to agree on frame boundaries one frame late (see oit_peer.cu).
+constexpr int PEER_FLAG_READY = 0;             // flags[READY + b] = n: band b allows frame n to be written into ITS buffer n & 1
+constexpr int PEER_FLAG_DONE  = PEER_MAX;      // flags[DONE + b]  = n: band b's strips of frame n are in THIS band's buffer n & 1
+constexpr int PEER_FLAG_SEQ   = 2 * PEER_MAX;  // frames this band has issued completely (local use); the running frame is SEQ + 1
+constexpr int PEER_FLAG_OVF   = 2 * PEER_MAX + 1;  // flags[OVF + (n & 1) * PEER_MAX + b] = n: band b's frame n overflowed a pair / clip buffer
+constexpr int PEER_FLAG_WORDS = 96;
+static_assert(PEER_FLAG_OVF + 2 * PEER_MAX <= PEER_FLAG_WORDS, "peer flag page");
 struct PeerTable
 {
-  uint32_t* frame[PEER_MAX];  // whole frame [H][W] BGRA8 of band b (peer-mapped, own entry local)
-  uint32_t* flags[PEER_MAX];  // PEER_FLAG_WORDS words next to it
+  uint32_t* frame[2][PEER_MAX];  // whole frames [H][W] BGRA8 of band b (peer-mapped, own entry local)
+  uint32_t* flags[PEER_MAX];     // PEER_FLAG_WORDS words behind them
 };
+// the frame buffer of every band the running frame is written to (device side)
+__device__ __forceinline__ uint32_t* const* peerFramesOfRunningFrame(const PeerTable* t, int bandIndex)
+{
+  const uint32_t n = *reinterpret_cast<volatile const uint32_t*>(t->flags[bandIndex] + PEER_FLAG_SEQ) + 1u;
+  return t->frame[n & 1u];
+}
 
 struct DeviceUbo
 {
@@ -238,13 +246,16 @@ PeerState*       peerCreate(int rank, int world, size_t frameBytes, void* handle
 int              peerOpen(PeerState* ps, const void* handles, std::string& err);  // world x 64 bytes, in band order
 void             peerClose(PeerState* ps);                                         // unmaps the other bands' buffers
 void             peerDestroy(PeerState* ps);
-uint32_t*        peerFrame(PeerState* ps);
+uint32_t*        peerFrame(PeerState* ps, unsigned which);  // this band's frame buffer `which` (0 / 1)
 const PeerTable* peerTable(PeerState* ps);
-int              peerSignal(PeerState* ps, int phase, const unsigned long long* stats, cudaStream_t s);
-int              peerWait(PeerState* ps, int phase, unsigned long long* stats, cudaStream_t s, uint32_t* zeroWord = nullptr);
+// first / last node of a frame's raster half, and the wait that completes the latest frame for the host (oit_peer.cu)
+int peerFrameBegin(PeerState* ps, unsigned long long* stats, uint32_t* zeroA, uint32_t* zeroB, cudaStream_t s);
+int peerFrameEnd(PeerState* ps, unsigned long long* stats, unsigned long long* hostMirror, int mirrorWords, const uint32_t* pairInfoA,
+                 const uint32_t* pairInfoB, cudaStream_t s);
+int peerFrameFlush(PeerState* ps, unsigned long long* stats, unsigned long long* hostMirror, cudaStream_t s);
 int peerScatterRows(PeerState* ps, const uint32_t* fin, int W, int localRows, int stripRows, cudaStream_t s);
 
-int launchClears(const FrameParams& p, int algorithm, cudaStream_t s);
+int launchClears(const FrameParams& p, int algorithm, cudaStream_t s, bool skipListHeads = false, bool skipCounter = false);
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s);
 int launchRasterLinkedList(const FrameParams& p, cudaStream_t s);  // oit_raster_ll.cu
 int launchRasterQueued(const FrameParams& p, int pass, cudaStream_t s);  // oit_raster_q.cu

@@ -105,6 +105,7 @@ __device__ __noinline__ void pushTiles(const FrameParams p)
   const uint32_t nWarps = (uint32_t)p.pushers * warpsPerCta, myWarp = blockIdx.x * warpsPerCta + (threadIdx.x >> 5);
   const int      stripRows = p.stripTileRows * TILE_H;
   const uint4*   fin4 = reinterpret_cast<const uint4*>(p.fin);
+  uint32_t* const* frames = peerFramesOfRunningFrame(p.peers, p.bandIndex);
   const int      quadsPerRow = p.W / 4;
   for(uint32_t slot = myWarp; slot < numTiles; slot += nWarps)
   {
@@ -139,7 +140,7 @@ __device__ __noinline__ void pushTiles(const FrameParams p)
         const int    strip = yl / stripRows;
         const size_t o     = (size_t)((strip * p.bandCount + p.bandIndex) * stripRows + (yl - strip * stripRows)) * quadsPerRow + xq;
         for(int b = 0; b < p.bandCount; b++)
-          reinterpret_cast<uint4*>(p.peers->frame[b])[o] = px;
+          reinterpret_cast<uint4*>(frames[b])[o] = px;
       }
     }
   }
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, llMinBlocks(S)) k_raster_ll(co
       if(emptyTile)
       {
         fusedClearTile(p, tileX0, yLocal0, tid);
+        if(ownValid)
+          p.aux[ownPix] = 0u;  // (the fused frame does not clear imgAux beforehand)
         publishTile(p, tile);
         return;
       }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, llMinBlocks(S)) k_raster_ll(co
     }
   }
   loadTables(tabs, p.tables);
-  headSm[tid] = (ownValid && !emptyTile) ? p.aux[ownPix] : 0u;
+  headSm[tid] = (ownValid && !emptyTile && !fused) ? p.aux[ownPix] : 0u;  // fused frame: every list starts empty
   if(!emptyTile)
   {
     pixSet[tid]            = make_uint4(0u, 0u, 0u, 0u);
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, llMinBlocks(S)) k_raster_ll(co
   }
 
   // the heads go to imgAux (the staged composite, dumps and a later colour pass read them there)
-  if(!emptyTile && ownValid)
+  if((!emptyTile || fused) && ownValid)
     p.aux[ownPix] = headSm[tid];
 
   // ---- fused frame: composite + resolve of the tile while its nodes are still in L1 / L2 ------------------------------------
