@@ -1008,7 +1008,7 @@ int oit_begin_frame(OitCtx* c)
   {
     // the fused linked-list frame kernel starts every list empty by itself (no imgAux clear), and in split-frame mode the
     // first node of the exchange (k_peer_frame_begin) resets the node counter
-    const bool leanLL = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading;
+    const bool leanLL = c->cfg.algorithm == OIT_LINKEDLIST && linkedListFrameStartsEmpty(c->fp);
     c->launches += launchClears(c->fp, (int)c->cfg.algorithm, c->stream, leanLL, leanLL && c->peers && c->peersOpen);
   }
   record(c, EV_CLEAR);
@@ -1112,7 +1112,7 @@ static int issueRaster(OitCtx* c)
   if(exchange)
   {
     // pusher CTAs: the linked-list frame kernel without sample shading / super-sampling (oit_raster_ll.cu)
-    const bool leanLL = c->fp.fused && c->cfg.algorithm == OIT_LINKEDLIST && !c->sampleShading;
+    const bool leanLL = c->cfg.algorithm == OIT_LINKEDLIST && linkedListFrameStartsEmpty(c->fp);
     const bool push   = leanLL && c->supersample == 1 && c->pushers > 0 && c->pushQueue.p != nullptr;
     c->fp.pushers     = push ? c->pushers : 0;
     c->fp.pushQueue   = (uint32_t*)c->pushQueue.p;

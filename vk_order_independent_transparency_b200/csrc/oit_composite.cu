@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) k_composite_sorted(const FrameParams p)
     const uint4* nodes  = reinterpret_cast<const uint4*>(p.abuf);
 #pragma unroll
     for(int i = 0; i < LMAX; i++)
-      if(offset != 0u && i < L)
+      if(offset != 0u && offset < p.capacity && i < L)
       {
         const uint4 e = nodes[offset];
         arr[i]        = Elem{e.x, e.y, e.z};
@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(128) k_composite_sorted(const FrameParams p)
       }
     bubbleSort<LMAX>(arr, n);
     Color4 tailColor = zeroColor();
-    while(offset != 0u)
+    // (a list cannot be longer than the pool: the bound keeps a corrupt A-buffer -- oit_upload of a foreign dump -- from
+    // spinning forever in a cycle; an index outside the pool ends the list)
+    for(uint32_t guard = p.capacity; offset != 0u && offset < p.capacity && guard != 0u; guard--)
     {
       const uint4 e = nodes[offset];
       const Elem  it{e.x, e.y, e.z};

@@ -208,7 +208,7 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
       {
         r.d[i]  = 0.f;
         r.ix[i] = (uint32_t)i;
-        if(offset != 0u && i < L)
+        if(offset != 0u && offset < p.capacity && i < L)
         {
           const uint4 e = nodes[offset];
           A.c[i][t] = e.x; r.d[i] = __uint_as_float(e.y); A.m[i][t] = e.z;
@@ -222,7 +222,8 @@ __device__ __forceinline__ Color4 fusedCompositeInvocation(const FrameParams& p,
       }
       fusedSortNetwork(r, n);
       Color4 tailColor = zeroColor();
-      while(offset != 0u)
+      // (a list cannot be longer than the pool: the bound keeps a corrupt A-buffer from spinning forever in a cycle)
+      for(uint32_t guard = p.capacity; offset != 0u && offset < p.capacity && guard != 0u; guard--)
       {
         const uint4    e   = nodes[offset];
         const uint32_t out = fusedInsertRegs(A, t, r, L, e.x, __uint_as_float(e.y), e.z);

@@ -258,6 +258,7 @@ int peerScatterRows(PeerState* ps, const uint32_t* fin, int W, int localRows, in
 int launchClears(const FrameParams& p, int algorithm, cudaStream_t s, bool skipListHeads = false, bool skipCounter = false);
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s);
 int launchRasterLinkedList(const FrameParams& p, cudaStream_t s);  // oit_raster_ll.cu
+bool linkedListFrameStartsEmpty(const FrameParams& p);             // oit_raster.cu: the fused frame goes to k_raster_ll
 int launchRasterQueued(const FrameParams& p, int pass, cudaStream_t s);  // oit_raster_q.cu
 int launchComposite(const FrameParams& p, int algorithm, cudaStream_t s);
 int launchResolve(const FrameParams& p, int supersample, int outW, int outLocalH, cudaStream_t s);

@@ -473,6 +473,9 @@ static void launchPass(const FrameParams& p, cudaStream_t s)
 static bool useLayered() { return getenv("OIT_B200_LAYERED") != nullptr; }
 static bool useLayeredLinkedList() { return useLayered() || getenv("OIT_B200_LAYERED_LL") != nullptr; }
 
+// the fused linked-list frame is rendered by k_raster_ll, which starts every list empty by itself (no imgAux clear needed)
+bool linkedListFrameStartsEmpty(const FrameParams& p) { return p.fused && !p.sampleShading && !useLayeredLinkedList(); }
+
 int launchRaster(const FrameParams& p, int pass, cudaStream_t s)
 {
   if(p.tilesX * p.tileRowsLocal == 0)
