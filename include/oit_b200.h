@@ -153,6 +153,10 @@ typedef struct OitCtx OitCtx;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
 int         oit_abi_version(void);
+/* host-only self check (no GPU needed): the sRGB8 encoder of the frame kernels (bucket table + one threshold) against its
+   definition (largest code whose threshold the value has reached) on every `stride`-th float of [0, 1] and on the special
+   values; stride 1 checks all 2^30 + 2^23 + 1 floats.  Returns 0; *mismatches must be 0. */
+int         oit_selfcheck_srgb_encoder(uint32_t stride, uint64_t* checked, uint64_t* mismatches);
 void        oit_default_config(OitConfig* cfg);                 /* State{} defaults, 1280x720, 1 band */
 int         oit_create(const OitConfig* cfg, OitCtx** out);     /* = updateRendererFromState(true,true), main.cpp:130-250 */
 int         oit_destroy(OitCtx* ctx);

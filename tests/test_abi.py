@@ -27,6 +27,17 @@ def test_library_exports_every_declared_symbol(oit_mod):
     assert lib.oit_abi_version() == 1
 
 
+def test_srgb_encoder_is_exact_for_every_float(oit_mod):
+    """The frame kernels encode linear -> sRGB8 with a bucket table + one threshold compare (oit_device.cuh: enc8) instead of
+    the GLSL's pow(); the library proves on the host that this equals the threshold definition for ALL floats in [0, 1]."""
+    lib = oit_mod.load_library()
+    lib.oit_selfcheck_srgb_encoder.argtypes = [C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.oit_selfcheck_srgb_encoder.restype = C.c_int
+    n, bad = C.c_uint64(), C.c_uint64()
+    assert lib.oit_selfcheck_srgb_encoder(1, C.byref(n), C.byref(bad)) == 0
+    assert n.value == 0x3F800000 + 1 + 11 and bad.value == 0
+
+
 def test_pod_layouts(oit_mod):
     assert C.sizeof(oit_mod.SceneData) == 224          # shaders/common.h:77-92 (std140)
     assert oit_mod.SceneData.viewport.offset == 192 and oit_mod.SceneData.linkedListAllocatedPerElement.offset == 204

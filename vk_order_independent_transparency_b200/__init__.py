@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "oit_draw_transparent", "oit_composite", "oit_resolve", "oit_synchronize", "oit_buffer_size", "oit_download",
     "oit_upload", "oit_device_ptr", "oit_read_color", "oit_get_stats", "oit_stream", "oit_local_row_to_global",
     "oit_band_gather_unique_id", "oit_enable_band_gather", "oit_band_peer_export", "oit_band_peer_enable",
-    "oit_band_peer_disable", "oit_generate_spheres", "oit_set_scene_spheres",
+    "oit_band_peer_disable", "oit_generate_spheres", "oit_set_scene_spheres", "oit_selfcheck_srgb_encoder",
 ]
 BUF_FRAME = 10
 STDLIB_LIBSTDCXX, STDLIB_MSVC = 0, 1  # OIT_CFG_SCENE_STDLIB: minstd_rand0 (libstdc++) or mt19937 (MSVC) scene RNG

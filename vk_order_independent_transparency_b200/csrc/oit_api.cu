@@ -8,6 +8,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "oit_internal.h"
@@ -410,6 +411,66 @@ extern "C" {
 static int finishFrame(OitCtx* c);
 
 int oit_abi_version(void) { return OIT_B200_ABI_VERSION; }
+
+// Host-only proof that the frame kernels' sRGB encoder (oit_device.cuh: enc8 -- the code of the value's bucket plus one
+// if the value has passed the bucket's one threshold) equals the definition (the largest k with c >= thr[k]) for EVERY
+// float in [0, 1] (stride 1: all 1,065,353,217 of them) and for the values outside, negative zero and NaN.
+int oit_selfcheck_srgb_encoder(uint32_t stride, uint64_t* checked, uint64_t* mismatches)
+{
+  if(stride == 0 || !checked || !mismatches)
+    return OIT_ERR_INVALID_ARG;
+  alignas(16) static unsigned char tableBytes[SRGB_TABLE_BYTES];
+  if(!buildTables(tableBytes))
+    return OIT_ERR_CUDA;
+  const float*         t      = reinterpret_cast<const float*>(tableBytes);
+  const unsigned char* bucket = tableBytes + SRGB_TABLE_FLOATS * 4;
+  auto                 device = [&](float c) -> uint32_t {  // enc8 of oit_device.cuh, statement for statement
+    const float cc = fminf(fmaxf(c, 0.f), 1.f);
+    uint32_t    bits;
+    memcpy(&bits, &cc, 4);
+    const uint32_t idx = std::max(bits >> 16, SRGB_BUCKET_BASE) - SRGB_BUCKET_BASE;
+    const uint32_t k   = bucket[idx];
+    return k + (cc >= t[TAB_THR + k + 1] ? 1u : 0u);
+  };
+  const uint32_t oneBits = 0x3F800000u;
+  const unsigned nThreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  std::vector<uint64_t>    bad(nThreads, 0), cnt(nThreads, 0);
+  std::vector<std::thread> pool;
+  for(unsigned w = 0; w < nThreads; w++)
+    pool.emplace_back([&, w]() {
+      const uint64_t span = ((uint64_t)oneBits + 1 + nThreads - 1) / nThreads;
+      uint64_t       b0 = w * span, b1 = std::min<uint64_t>((uint64_t)oneBits + 1, b0 + span);
+      b0 += (stride - b0 % stride) % stride;
+      for(uint64_t b = b0; b < b1; b += stride)
+      {
+        const uint32_t bits = (uint32_t)b;
+        float          c;
+        memcpy(&c, &bits, 4);
+        bad[w] += device(c) != hostEnc8(t, c);
+        cnt[w]++;
+      }
+    });
+  for(auto& th : pool)
+    th.join();
+  uint64_t nBad = 0, n = 0;
+  for(unsigned w = 0; w < nThreads; w++)
+  {
+    nBad += bad[w];
+    n += cnt[w];
+  }
+  const float specials[] = {-0.f, -1.f, 1.0000001f, 2.f, 1e30f, -1e30f, std::numeric_limits<float>::infinity(), -std::numeric_limits<float>::infinity(),
+                            std::numeric_limits<float>::quiet_NaN(), 1e-45f, 1.17549435e-38f};
+  for(float c : specials)
+  {
+    // the definition on a clamped value (NaN -> 0, as fminf(fmaxf(c, 0), 1) does)
+    const float cc = c != c ? 0.f : std::min(std::max(c, 0.f), 1.f);
+    nBad += device(c) != hostEnc8(t, cc);
+    n++;
+  }
+  *checked    = n;
+  *mismatches = nBad;
+  return OIT_OK;
+}
 
 void oit_default_config(OitConfig* cfg)
 {

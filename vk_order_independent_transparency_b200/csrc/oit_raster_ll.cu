@@ -14,8 +14,8 @@
 //                 bits; node = pixel's first node + rank; next = node - 1 (rank > 0) or the pixel's previous head.  Shade,
 //                 pack, ONE 128-bit store.  No tickets, no layers, no per-fragment atomics, no barrier per layer.
 //
-// Two CTA barriers per batch of up to 1024 candidates (after A, after B; sets and lists are double-buffered so that C of one
-// batch overlaps A of the next).  The list heads of the tile live in shared memory for the whole pass (written to imgAux
+// Two CTA barriers per batch of 2048 candidates (two coverage rounds; after A, after B; sets and lists are double-buffered
+// so that C of one batch overlaps A of the next).  The list heads of the tile live in shared memory for the whole pass (written to imgAux
 // once at the end); the lists are identical to the ones the sequential schedule builds (same nodes per pixel in the same
 // link order; node NUMBERS differ, like between any two runs of the reference).
 //
