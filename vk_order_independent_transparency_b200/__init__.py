@@ -436,7 +436,8 @@ class Sample:
 
     def enableBandPeers(self, dist=None):
         """Split frame over NVLink peer memory: the frame kernel of onRender stores its resolved pixels straight into the
-        frame buffer of EVERY band (CUDA IPC mappings), two flag rounds per frame keep the bands in step.  Collective over
+        frame buffers of EVERY band (CUDA IPC mappings; two per band, frames alternate), and two flag rounds per frame keep the
+        bands in step one frame late (synchronize() / readFrame() / frameDevice() after synchronize() see the latest frame).  Collective over
         the bandCount ranks; `dist` = an initialised torch.distributed, used only to exchange the 64-byte IPC handles.
         Returns False (on every rank, nothing enabled) when some rank cannot map its peers: use enableBandGather then."""
         if dist is None:
@@ -461,7 +462,10 @@ class Sample:
         return False
 
     def frameDevice(self):
-        """The gathered full frame (uint32 BGRA8 [height, width]) as a __cuda_array_interface__ object (zero copy)."""
+        """The gathered full frame (uint32 BGRA8 [height, width]) as a __cuda_array_interface__ object (zero copy).  Completes
+        the latest frame first (with the peer exchange the frames alternate between two buffers, and the pointer is the one
+        of the latest COMPLETED frame); valid until the next onRender."""
+        self.synchronize()
         ptr = self.L.oit_device_ptr(self.h, BUF_FRAME)
         return _DeviceArray(ptr, (self.height, self.width), "<i4", self) if ptr else None
 
