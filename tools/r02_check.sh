@@ -9,6 +9,6 @@ OIT_B200_NO_PIPELINE=1 python bench.py --steps 40 --warmup 5 --no-table --no-cpu
 python - <<EOF
 import json
 for f in ("${TAG}_bench","${TAG}_bench_nopipe"):
-    d=json.load(open("gpurun_out/%s.json"%f)); print(f, round(d["ms_per_step"],4), d["stages"]["geometry"]["ms"], d["stages"]["clear"]["ms"], d["stages"]["color"]["ms"], d["gpu_launches"]/d["steps"], round(d["e2e"]["ms_per_step"],3), round(d["e2e"]["instanced"]["ms_per_step"],3))
+    d=json.load(open("gpurun_out/%s.json"%f)); print(f, round(d["ms_per_step"],4), d["stages"]["geometry"]["ms"], d["stages"]["clear"]["ms"], d["stages"]["color"]["ms"], d["gpu_launches"]/d["steps"], round(d["e2e"]["ms_per_step"],3), round(d["e2e"]["flattened_mesh"]["ms_per_step"],3))
 EOF
 tail -3 gpurun_out/${TAG}_bench.err

@@ -8,7 +8,7 @@ for n in $NS; do
 import json
 try:
     d = json.load(open("gpurun_out/${TAG}_${WL}_n$n.json"))
-    print("n=$n", round(d["ms_per_step"], 4), "stages", {k: v["ms"] for k, v in d["stages"].items()}, "e2e", round(d["e2e"]["ms_per_step"], 3), round(d["e2e"]["instanced"]["ms_per_step"], 3), d["config"]["band_gather_verified"], d.get("exchange_wait"))
+    print("n=$n", round(d["ms_per_step"], 4), "stages", {k: v["ms"] for k, v in d["stages"].items()}, "e2e", round(d["e2e"]["ms_per_step"], 3), round(d["e2e"]["flattened_mesh"]["ms_per_step"], 3), d["config"]["band_gather_verified"], d.get("exchange_wait"))
 except Exception as e:
     print("n=$n failed", e)
 EOF2
